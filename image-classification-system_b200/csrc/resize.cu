@@ -1,0 +1,524 @@
+// Separable antialiased BILINEAR resize + normalise (thumbnail / preview tensor), sm_100a.
+//
+// The reference has no resize; BASELINE.json configs 1,2,3,5 require
+// "hash + 256x256 thumbnail".  Semantics = Pillow's 8-bit two-pass resampler (the reference's
+// pinned image library, requirements.txt:9), reproduced bit-exactly:
+//   per axis: scale = in/out; support = max(scale,1); ksize = 2*ceil(support)+1;
+//   triangle weights in float64 normalised by their sequential sum, quantised to 22-bit
+//   fixed point (int(0.5 + w * 2^22)); out = clip8((2^21 + sum px*k) >> 22);
+//   HORIZONTAL pass first into a uint8 intermediate, then the VERTICAL pass.
+//
+// resize_bands_kernel<KSH> — the product kernel.  One CTA = one band of output rows of one
+// image.  The band's input rows are a single contiguous byte range of the HWC image; the
+// bulk-copy (TMA) engine streams it through a ring of shared-memory stages (cp.async.bulk +
+// mbarrier), so global memory is read once, in large aligned bursts, with no register
+// staging.  Thread x owns output column x: its KSH horizontal taps live in registers for the
+// whole band; per input row it pulls its ~3*KSH source bytes from shared memory as 32-bit
+// words, funnel-shifts them to a byte-aligned window and runs the integer MACs, writing the
+// 3-byte intermediate into a shared-memory tile.  After the last stage the CTA runs the
+// vertical pass out of that tile and writes the uint8 HWC thumbnail (32-bit stores) and the
+// float32 CHW preview.  No tensor cores: 2 MAC per input byte, nothing to contract.
+//
+// resize_generic_kernel — any shape / any alignment, one thread per output pixel, straight
+// from global memory.  Used when the fast path's limits do not hold, and by the tests as an
+// independent device implementation.
+#include "common.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace b2 {
+
+constexpr int kPrecisionBits = 32 - 8 - 2;
+constexpr int kRound = 1 << (kPrecisionBits - 1);
+
+// ---------------------------------------------------------------------------------------
+// Host: tap tables, identical arithmetic (float64, same operation order) to Pillow.
+// ---------------------------------------------------------------------------------------
+struct AxisTaps {
+    int ksize = 0;
+    std::vector<int32_t> bounds;   // out x {first, count}
+    std::vector<int32_t> coeffs;   // out x ksize
+};
+
+static AxisTaps make_taps(int in_size, int out_size) {
+    AxisTaps t;
+    const double scale = double(in_size) / double(out_size);
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = 1.0 * filterscale;
+    t.ksize = int(std::ceil(support)) * 2 + 1;
+    t.bounds.assign(size_t(out_size) * 2, 0);
+    t.coeffs.assign(size_t(out_size) * t.ksize, 0);
+    std::vector<double> w(t.ksize);
+    const double ss = 1.0 / filterscale;
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = (xx + 0.5) * scale;
+        int xmin = int(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = int(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        const int n = xmax - xmin;
+        double ww = 0.0;
+        for (int x = 0; x < n; ++x) {
+            double a = (x + xmin - center + 0.5) * ss;
+            if (a < 0.0) a = -a;
+            const double v = a < 1.0 ? 1.0 - a : 0.0;
+            w[x] = v;
+            ww += v;
+        }
+        for (int x = 0; x < n; ++x) {
+            double v = w[x];
+            if (ww != 0.0) v /= ww;
+            t.coeffs[size_t(xx) * t.ksize + x] =
+                v < 0 ? int(-0.5 + v * (1 << kPrecisionBits)) : int(0.5 + v * (1 << kPrecisionBits));
+        }
+        t.bounds[2 * xx] = xmin;
+        t.bounds[2 * xx + 1] = n;
+    }
+    return t;
+}
+
+}  // namespace b2
+
+struct b2_resize_plan {
+    int in_h, in_w, out_h, out_w;
+    b2::AxisTaps h, v;
+    int device;
+    int32_t *d_hbounds, *d_hcoeffs, *d_vbounds, *d_vcoeffs;
+    // fast-path geometry
+    int band_rows;        // output rows per CTA
+    int n_bands;
+    int max_band_in_rows; // max input rows any band needs
+    int rows_per_stage;
+    int stage_bytes;      // bytes of one ring stage (incl. alignment + over-read padding)
+    int n_stages;
+    int tmp_pitch;        // bytes per intermediate row (multiple of 16)
+    int threads;
+    int ksh_bucket;       // template bucket for horizontal taps (0 = fast path unavailable)
+    size_t smem_bytes;
+};
+
+namespace b2 {
+
+constexpr int kMaxStages = 4;
+
+struct ResizeParams {
+    const uint8_t *rgb;
+    const uint64_t *offsets;
+    const uint32_t *out_slot;
+    uint8_t *thumb;
+    float *preview;
+    const int32_t *hbounds, *hcoeffs, *vbounds, *vcoeffs;
+    int in_h, in_w, out_h, out_w;
+    int ksize_h, ksize_v;
+    int band_rows, n_bands, max_band_in_rows;
+    int rows_per_stage, stage_bytes, n_stages, tmp_pitch;
+    float mean[3], inv_std[3];
+};
+
+__device__ __forceinline__ uint32_t clip8(int32_t acc) {
+    const int32_t v = acc >> kPrecisionBits;
+    return uint32_t(min(max(v, 0), 255));
+}
+
+// (u8 * (1/255) - mean) * inv_std as three separately rounded float32 operations (no FMA
+// contraction), so the preview is bit-identical to the NumPy oracle.
+__device__ __forceinline__ float normalise(uint32_t u8, float mean, float inv_std) {
+    return __fmul_rn(__fsub_rn(__fmul_rn(float(u8), 1.0f / 255.0f), mean), inv_std);
+}
+
+template <int KSH>
+__global__ void __launch_bounds__(256)
+resize_bands_kernel(const ResizeParams p) {
+    constexpr int NV = (3 * KSH + 3) / 4;       // byte-aligned window, in 32-bit words
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+
+    const int tid = threadIdx.x;
+    const int img = blockIdx.x / p.n_bands;
+    const int band = blockIdx.x - img * p.n_bands;
+    const int oy0 = band * p.band_rows;
+    const int oy1 = min(oy0 + p.band_rows, p.out_h);
+    const int r0 = p.vbounds[2 * oy0];
+    const int r1 = p.vbounds[2 * (oy1 - 1)] + p.vbounds[2 * (oy1 - 1) + 1];
+    const int n_rows = r1 - r0;
+    const int pitch = p.in_w * 3;
+    const uint64_t img_off = p.offsets[img];
+    const uint8_t *img_ptr = p.rgb + img_off;
+    const uint64_t img_bytes = uint64_t(p.in_h) * pitch;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(img_ptr)) & 15) == 0;
+
+    uint8_t *ring = smem;                                            // n_stages * stage_bytes
+    uint8_t *tmp = smem + size_t(p.n_stages) * p.stage_bytes;        // max_band_in_rows * tmp_pitch
+    int32_t *vb_s = reinterpret_cast<int32_t *>(tmp + size_t(p.max_band_in_rows) * p.tmp_pitch);  // band_rows*2
+    int32_t *vk_s = vb_s + 2 * p.band_rows;                          // band_rows * ksize_v
+
+    if (tid == 0) {
+        for (int s = 0; s < p.n_stages; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    // vertical taps of this band -> shared memory
+    for (int i = tid; i < (oy1 - oy0) * 2; i += blockDim.x) vb_s[i] = p.vbounds[2 * oy0 + i];
+    for (int i = tid; i < (oy1 - oy0) * p.ksize_v; i += blockDim.x) vk_s[i] = p.vcoeffs[oy0 * p.ksize_v + i];
+
+    // horizontal taps of my column -> registers
+    const bool col_active = tid < p.out_w;
+    int xmin = 0;
+    int32_t kh[KSH];
+#pragma unroll
+    for (int t = 0; t < KSH; ++t) kh[t] = 0;
+    if (col_active) {
+        xmin = p.hbounds[2 * tid];
+#pragma unroll
+        for (int t = 0; t < KSH; ++t)
+            if (t < p.ksize_h) kh[t] = p.hcoeffs[tid * p.ksize_h + t];
+    }
+    __syncthreads();
+
+    const int total_stages = (n_rows + p.rows_per_stage - 1) / p.rows_per_stage;
+
+    // Stage s covers input rows [r0 + s*RPS, min(r0 + (s+1)*RPS, r1)) = bytes [b0, b1) of the
+    // image.  The copy engine moves the enclosing 16-byte aligned range [a0, a1), clamped to
+    // the last whole 16-byte unit of the image; a ragged tail (< 16 B, last rows of the image
+    // only) is patched with ordinary loads.
+    auto stage_range = [&](int s, uint64_t &b0, uint64_t &b1) {
+        const int ra = r0 + s * p.rows_per_stage;
+        const int rb = min(ra + p.rows_per_stage, r1);
+        b0 = uint64_t(ra) * pitch;
+        b1 = uint64_t(rb) * pitch;
+    };
+    auto issue = [&](int s) {          // thread 0 only, aligned images only
+        uint64_t b0, b1;
+        stage_range(s, b0, b1);
+        const uint64_t a0 = b0 & ~uint64_t(15);
+        uint64_t a1 = (b1 + 15) & ~uint64_t(15);
+        const uint64_t lim = img_bytes & ~uint64_t(15);
+        if (a1 > lim) a1 = lim;
+        const int buf = s % p.n_stages;
+        const uint32_t bytes = a1 > a0 ? uint32_t(a1 - a0) : 0u;
+        if (bytes) {
+            mbar_arrive_expect_tx(&full_bar[buf], bytes);
+            bulk_g2s(ring + size_t(buf) * p.stage_bytes, img_ptr + a0, bytes, &full_bar[buf]);
+        } else {
+            mbar_arrive(&full_bar[buf]);
+        }
+    };
+
+    if (aligned && tid == 0) {
+        for (int s = 0; s < p.n_stages - 1 && s < total_stages; ++s) issue(s);
+    }
+
+    for (int s = 0; s < total_stages; ++s) {
+        const int buf = s % p.n_stages;
+        uint8_t *sbuf = ring + size_t(buf) * p.stage_bytes;
+        uint64_t b0, b1;
+        stage_range(s, b0, b1);
+        const uint64_t a0 = b0 & ~uint64_t(15);
+        if (aligned) {
+            if (tid == 0 && s + p.n_stages - 1 < total_stages) issue(s + p.n_stages - 1);
+            mbar_wait(&full_bar[buf], uint32_t((s / p.n_stages) & 1));
+            const uint64_t lim = img_bytes & ~uint64_t(15);
+            if (b1 > lim) {            // ragged image tail: uniform branch, last stage of last band
+                for (uint64_t b = max(lim, a0) + tid; b < b1; b += blockDim.x) sbuf[b - a0] = img_ptr[b];
+                __syncthreads();
+            }
+        } else {                       // misaligned image: cooperative copy, same smem layout
+            for (uint64_t b = b0 + tid; b < b1; b += blockDim.x) sbuf[b - a0] = img_ptr[b];
+            __syncthreads();
+        }
+
+        const int ra = r0 + s * p.rows_per_stage;
+        const int rb = min(ra + p.rows_per_stage, r1);
+        if (col_active) {
+            for (int r = ra; r < rb; ++r) {
+                // byte address (in shared memory) of my first source byte
+                const uint32_t src = smem_u32(sbuf) + uint32_t(uint64_t(r) * pitch - a0) + 3u * xmin;
+                const uint32_t base = src & ~3u;
+                const uint32_t sh = (src & 3u) * 8u;
+                uint32_t w[NV + 1];
+#pragma unroll
+                for (int j = 0; j < NV + 1; ++j)
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[j]) : "r"(base + 4u * j));
+                uint32_t v[NV];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) v[j] = __funnelshift_r(w[j], w[j + 1], sh);
+                int32_t acc0 = kRound, acc1 = kRound, acc2 = kRound;
+#pragma unroll
+                for (int t = 0; t < KSH; ++t) {
+                    const int q0 = 3 * t, q1 = 3 * t + 1, q2 = 3 * t + 2;
+                    acc0 += int32_t(__byte_perm(v[q0 >> 2], 0, 0x4440 | (q0 & 3))) * kh[t];
+                    acc1 += int32_t(__byte_perm(v[q1 >> 2], 0, 0x4440 | (q1 & 3))) * kh[t];
+                    acc2 += int32_t(__byte_perm(v[q2 >> 2], 0, 0x4440 | (q2 & 3))) * kh[t];
+                }
+                uint8_t *dst = tmp + size_t(r - r0) * p.tmp_pitch + 3 * tid;
+                dst[0] = uint8_t(clip8(acc0));
+                dst[1] = uint8_t(clip8(acc1));
+                dst[2] = uint8_t(clip8(acc2));
+            }
+        }
+        __syncthreads();               // stage consumed (ring slot reusable), tmp rows visible
+    }
+
+    // ---- vertical pass out of the shared-memory intermediate -----------------------------
+    const int row_bytes = p.out_w * 3;
+    const int row_words = (row_bytes + 3) >> 2;
+    const uint32_t slot = p.out_slot ? p.out_slot[img] : uint32_t(img);
+    uint8_t *thumb = p.thumb + uint64_t(slot) * p.out_h * row_bytes;
+    float *prev = p.preview ? p.preview + uint64_t(slot) * 3 * p.out_h * p.out_w : nullptr;
+    const bool word_store = ((reinterpret_cast<uintptr_t>(thumb) | uint32_t(row_bytes)) & 3) == 0;
+    const int items = (oy1 - oy0) * row_words;
+    for (int it = tid; it < items; it += blockDim.x) {
+        const int ly = it / row_words;
+        const int wj = it - ly * row_words;
+        const int oy = oy0 + ly;
+        const int ymin = vb_s[2 * ly], cnt = vb_s[2 * ly + 1];
+        const int32_t *vk = vk_s + ly * p.ksize_v;
+        int32_t a0 = kRound, a1 = kRound, a2 = kRound, a3 = kRound;
+        const uint8_t *col = tmp + size_t(ymin - r0) * p.tmp_pitch + 4 * wj;
+        for (int t = 0; t < cnt; ++t) {
+            const uint32_t px = *reinterpret_cast<const uint32_t *>(col + size_t(t) * p.tmp_pitch);
+            const int32_t k = vk[t];
+            a0 += int32_t(px & 0xffu) * k;
+            a1 += int32_t((px >> 8) & 0xffu) * k;
+            a2 += int32_t((px >> 16) & 0xffu) * k;
+            a3 += int32_t(px >> 24) * k;
+        }
+        const uint32_t o[4] = {clip8(a0), clip8(a1), clip8(a2), clip8(a3)};
+        const int b_first = 4 * wj;
+        const int nb = min(4, row_bytes - b_first);
+        uint8_t *trow = thumb + size_t(oy) * row_bytes + b_first;
+        if (word_store && nb == 4) {
+            *reinterpret_cast<uint32_t *>(trow) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        } else {
+            for (int i = 0; i < nb; ++i) trow[i] = uint8_t(o[i]);
+        }
+        if (prev) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < nb) {
+                    const int b = b_first + i;
+                    const int px_x = b / 3, ch = b - 3 * px_x;
+                    prev[(size_t(ch) * p.out_h + oy) * p.out_w + px_x] = normalise(o[i], p.mean[ch], p.inv_std[ch]);
+                }
+            }
+        }
+    }
+}
+
+// One thread per output pixel (all three channels), any shape, any alignment.
+__global__ void __launch_bounds__(256)
+resize_generic_kernel(const ResizeParams p, uint32_t n) {
+    const uint64_t gid = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    const uint64_t per_img = uint64_t(p.out_h) * p.out_w;
+    if (gid >= per_img * n) return;
+    const uint32_t img = uint32_t(gid / per_img);
+    const uint32_t rem = uint32_t(gid - img * per_img);
+    const int oy = rem / p.out_w, ox = rem - oy * p.out_w;
+    const uint8_t *src = p.rgb + p.offsets[img];
+    const int pitch = p.in_w * 3;
+    const int xmin = p.hbounds[2 * ox], xcnt = p.hbounds[2 * ox + 1];
+    const int ymin = p.vbounds[2 * oy], ycnt = p.vbounds[2 * oy + 1];
+    const int32_t *kh = p.hcoeffs + size_t(ox) * p.ksize_h;
+    const int32_t *kv = p.vcoeffs + size_t(oy) * p.ksize_v;
+    int32_t v0 = kRound, v1 = kRound, v2 = kRound;
+    for (int ty = 0; ty < ycnt; ++ty) {
+        const uint8_t *row = src + size_t(ymin + ty) * pitch + 3 * xmin;
+        int32_t h0 = kRound, h1 = kRound, h2 = kRound;
+        for (int tx = 0; tx < xcnt; ++tx) {
+            const int32_t k = kh[tx];
+            h0 += int32_t(row[3 * tx]) * k;
+            h1 += int32_t(row[3 * tx + 1]) * k;
+            h2 += int32_t(row[3 * tx + 2]) * k;
+        }
+        const int32_t k = kv[ty];
+        v0 += int32_t(clip8(h0)) * k;        // uint8 intermediate, as Pillow stores it
+        v1 += int32_t(clip8(h1)) * k;
+        v2 += int32_t(clip8(h2)) * k;
+    }
+    const uint32_t o[3] = {clip8(v0), clip8(v1), clip8(v2)};
+    const uint32_t slot = p.out_slot ? p.out_slot[img] : img;
+    uint8_t *t = p.thumb + (uint64_t(slot) * per_img + rem) * 3;
+    t[0] = uint8_t(o[0]); t[1] = uint8_t(o[1]); t[2] = uint8_t(o[2]);
+    if (p.preview) {
+        float *pv = p.preview + uint64_t(slot) * 3 * per_img + rem;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            pv[size_t(c) * per_img] = normalise(o[c], p.mean[c], p.inv_std[c]);
+    }
+}
+
+static int pick_bucket(int ksize_h) {
+    const int buckets[] = {3, 5, 9, 13, 17, 25, 33};
+    for (int b : buckets)
+        if (ksize_h <= b) return b;
+    return 0;
+}
+
+template <int KSH>
+static cudaError_t set_smem_attr(size_t bytes) {
+    return cudaFuncSetAttribute(resize_bands_kernel<KSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+}
+
+template <int KSH>
+static void launch_bands(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st) {
+    resize_bands_kernel<KSH><<<n * uint32_t(p.n_bands), threads, smem, st>>>(p);
+}
+
+}  // namespace b2
+
+extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b2_resize_plan **plan_out) {
+    using namespace b2;
+    B2_REQUIRE(plan_out != nullptr, "b2_resize_plan_create: null output");
+    B2_REQUIRE(in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0, "b2_resize_plan_create: non-positive dimension");
+    B2_REQUIRE(in_h <= 65536 && in_w <= 65536 && out_h <= 16384 && out_w <= 16384, "b2_resize_plan_create: dimension too large");
+    b2_resize_plan *pl = new b2_resize_plan();
+    pl->in_h = in_h; pl->in_w = in_w; pl->out_h = out_h; pl->out_w = out_w;
+    pl->h = make_taps(in_w, out_w);
+    pl->v = make_taps(in_h, out_h);
+    B2_CUDA_CHECK(cudaGetDevice(&pl->device));
+    auto upload = [](const std::vector<int32_t> &v, int32_t **d) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, v.size() * sizeof(int32_t));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*d, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    };
+    B2_CUDA_CHECK(upload(pl->h.bounds, &pl->d_hbounds));
+    B2_CUDA_CHECK(upload(pl->h.coeffs, &pl->d_hcoeffs));
+    B2_CUDA_CHECK(upload(pl->v.bounds, &pl->d_vbounds));
+    B2_CUDA_CHECK(upload(pl->v.coeffs, &pl->d_vcoeffs));
+
+    // ---- fast-path geometry -----------------------------------------------------------
+    pl->ksh_bucket = pick_bucket(pl->h.ksize);
+    pl->threads = ((out_w + 31) / 32) * 32;
+    if (pl->threads > 256) pl->ksh_bucket = 0;           // thread-per-column layout: out_w <= 256
+    const int pitch = in_w * 3;
+    pl->tmp_pitch = ((out_w * 3 + 15) / 16) * 16;
+    // stage: ~16 KB of rows; over-read padding = the widest register window + alignment slack
+    int rps = 16384 / pitch;
+    if (rps < 1) rps = 1;
+    if (rps > 32) rps = 32;
+    pl->rows_per_stage = rps;
+    const int overread = 3 * 33 + 64;
+    pl->stage_bytes = ((rps * pitch + 32 + overread + 127) / 128) * 128;
+    pl->n_stages = 3;
+    // band height: intermediate tile <= ~48 KB, at least 1 row, at most 32
+    const size_t budget = 200 * 1024;
+    int best = 0;
+    for (int br = 32; br >= 1; --br) {
+        int max_rows = 0;
+        for (int oy0 = 0; oy0 < out_h; oy0 += br) {
+            const int oy1 = (oy0 + br < out_h ? oy0 + br : out_h) - 1;
+            const int rows = pl->v.bounds[2 * oy1] + pl->v.bounds[2 * oy1 + 1] - pl->v.bounds[2 * oy0];
+            if (rows > max_rows) max_rows = rows;
+        }
+        const size_t tile = size_t(max_rows) * pl->tmp_pitch;
+        const size_t total = size_t(pl->n_stages) * pl->stage_bytes + tile + size_t(br) * (2 + pl->v.ksize) * 4 + 64;
+        if ((tile <= 48 * 1024 || br == 1) && total <= budget) {
+            best = br;
+            pl->max_band_in_rows = max_rows;
+            pl->smem_bytes = total;
+            break;
+        }
+    }
+    if (best == 0) pl->ksh_bucket = 0;
+    pl->band_rows = best > 0 ? best : 1;
+    pl->n_bands = (out_h + pl->band_rows - 1) / pl->band_rows;
+    *plan_out = pl;
+    return B2_OK;
+}
+
+extern "C" int b2_resize_plan_destroy(b2_resize_plan *pl) {
+    if (!pl) return B2_OK;
+    cudaFree(pl->d_hbounds); cudaFree(pl->d_hcoeffs); cudaFree(pl->d_vbounds); cudaFree(pl->d_vcoeffs);
+    delete pl;
+    return B2_OK;
+}
+
+extern "C" int b2_resize_plan_taps(const b2_resize_plan *pl, int axis, int *ksize, int32_t *h_bounds,
+                                   int32_t *h_coeffs, uint64_t coeffs_capacity) {
+    using namespace b2;
+    B2_REQUIRE(pl && ksize, "b2_resize_plan_taps: null pointer");
+    B2_REQUIRE(axis == 0 || axis == 1, "b2_resize_plan_taps: axis must be 0 or 1");
+    const AxisTaps &t = axis == 0 ? pl->h : pl->v;
+    *ksize = t.ksize;
+    if (h_bounds) memcpy(h_bounds, t.bounds.data(), t.bounds.size() * sizeof(int32_t));
+    if (h_coeffs) {
+        B2_REQUIRE(coeffs_capacity >= t.coeffs.size(), "b2_resize_plan_taps: coeffs buffer too small");
+        memcpy(h_coeffs, t.coeffs.data(), t.coeffs.size() * sizeof(int32_t));
+    }
+    return B2_OK;
+}
+
+// B2_RESIZE_PATH: 0 = auto, 1 = force generic kernel (tests / comparison).
+static int resize_path_override() {
+    const char *e = getenv("B2_RESIZE_PATH");
+    return e ? atoi(e) : 0;
+}
+
+extern "C" int b2_resize_normalize_batch(const b2_resize_plan *pl, const uint8_t *d_rgb,
+                                         const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,
+                                         uint8_t *d_thumb, float *d_preview, const float mean[3],
+                                         const float inv_std[3], void *stream) {
+    using namespace b2;
+    if (n == 0) return B2_OK;
+    B2_REQUIRE(pl && d_rgb && d_offsets && d_thumb, "b2_resize_normalize_batch: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ResizeParams p;
+    p.rgb = d_rgb; p.offsets = d_offsets; p.out_slot = d_out_slot; p.thumb = d_thumb; p.preview = d_preview;
+    p.hbounds = pl->d_hbounds; p.hcoeffs = pl->d_hcoeffs; p.vbounds = pl->d_vbounds; p.vcoeffs = pl->d_vcoeffs;
+    p.in_h = pl->in_h; p.in_w = pl->in_w; p.out_h = pl->out_h; p.out_w = pl->out_w;
+    p.ksize_h = pl->h.ksize; p.ksize_v = pl->v.ksize;
+    p.band_rows = pl->band_rows; p.n_bands = pl->n_bands; p.max_band_in_rows = pl->max_band_in_rows;
+    p.rows_per_stage = pl->rows_per_stage; p.stage_bytes = pl->stage_bytes; p.n_stages = pl->n_stages;
+    p.tmp_pitch = pl->tmp_pitch;
+    for (int c = 0; c < 3; ++c) {
+        p.mean[c] = mean ? mean[c] : 0.0f;
+        p.inv_std[c] = inv_std ? inv_std[c] : 1.0f;
+    }
+    const bool fast = pl->ksh_bucket != 0 && resize_path_override() != 1 &&
+                      uint64_t(n) * uint64_t(pl->n_bands) < 0x7fffffffull;
+    if (!fast) {
+        const uint64_t threads = uint64_t(n) * pl->out_h * pl->out_w;
+        B2_REQUIRE((threads + 255) / 256 < 0x7fffffffull, "b2_resize_normalize_batch: batch too large");
+        resize_generic_kernel<<<unsigned((threads + 255) / 256), 256, 0, st>>>(p, n);
+        B2_LAUNCH_CHECK("resize_generic_kernel");
+        return B2_OK;
+    }
+    static std::mutex mu;
+    static size_t attr_bytes[64][8];     // [device][bucket index]: largest smem opt-in done so far
+    int bi = 0;
+    cudaError_t e = cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        switch (pl->ksh_bucket) {
+            case 3: bi = 0; break; case 5: bi = 1; break; case 9: bi = 2; break; case 13: bi = 3; break;
+            case 17: bi = 4; break; case 25: bi = 5; break; default: bi = 6; break;
+        }
+        const int dev = pl->device & 63;
+        if (attr_bytes[dev][bi] < pl->smem_bytes) {
+            switch (pl->ksh_bucket) {
+                case 3: e = set_smem_attr<3>(pl->smem_bytes); break;
+                case 5: e = set_smem_attr<5>(pl->smem_bytes); break;
+                case 9: e = set_smem_attr<9>(pl->smem_bytes); break;
+                case 13: e = set_smem_attr<13>(pl->smem_bytes); break;
+                case 17: e = set_smem_attr<17>(pl->smem_bytes); break;
+                case 25: e = set_smem_attr<25>(pl->smem_bytes); break;
+                default: e = set_smem_attr<33>(pl->smem_bytes); break;
+            }
+            if (e == cudaSuccess) attr_bytes[dev][bi] = pl->smem_bytes;
+        }
+    }
+    B2_CUDA_CHECK(e);
+    switch (pl->ksh_bucket) {
+        case 3: launch_bands<3>(p, n, pl->threads, pl->smem_bytes, st); break;
+        case 5: launch_bands<5>(p, n, pl->threads, pl->smem_bytes, st); break;
+        case 9: launch_bands<9>(p, n, pl->threads, pl->smem_bytes, st); break;
+        case 13: launch_bands<13>(p, n, pl->threads, pl->smem_bytes, st); break;
+        case 17: launch_bands<17>(p, n, pl->threads, pl->smem_bytes, st); break;
+        case 25: launch_bands<25>(p, n, pl->threads, pl->smem_bytes, st); break;
+        default: launch_bands<33>(p, n, pl->threads, pl->smem_bytes, st); break;
+    }
+    B2_LAUNCH_CHECK("resize_bands_kernel");
+    return B2_OK;
+}

@@ -1,0 +1,357 @@
+// Batched multi-message SHA-256 (FIPS 180-4) for sm_100a.
+//
+// Replaces hashlib.sha256(data).hexdigest() of the reference
+// (app/services/webdav_sync.py:59, app/services/activity_api_sync.py:798,
+//  app/api/routes/images.py:62) for a whole batch of file buffers.
+//
+// SHA-256 is a serial chain per message (Merkle-Damgard), so the only parallelism is ACROSS
+// messages: one lane owns one message and runs the 64-round compression in registers; a
+// warp owns 32 messages (sorted by length by the caller so lanes finish together).  The
+// kernel is bound by the INT32 ALU pipe (~1400 LOP3/SHF/IADD3 per 64-byte block), not by
+// HBM — see DESIGN.md "sha256_lanes".
+//
+// Two load paths:
+//   sha256_lanes_kernel   — each lane streams its own message with 128-bit loads (four per
+//                           64-byte block, prefetched one block ahead).  Every 32-byte
+//                           sector fetched is fully used, so DRAM traffic = message bytes.
+//   sha256_staged_kernel  — the warp's 32 messages are staged through shared memory by the
+//                           bulk-copy engine (cp.async.bulk, one 1-D copy per lane per
+//                           stage, mbarrier-tracked), double buffered, and each lane
+//                           compresses from its own padded shared-memory row.
+#include "common.cuh"
+
+namespace b2 {
+
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+#define B2_BSIG0(x) (rotr32(x, 2) ^ rotr32(x, 13) ^ rotr32(x, 22))
+#define B2_BSIG1(x) (rotr32(x, 6) ^ rotr32(x, 11) ^ rotr32(x, 25))
+#define B2_SSIG0(x) (rotr32(x, 7) ^ rotr32(x, 18) ^ ((x) >> 3))
+#define B2_SSIG1(x) (rotr32(x, 17) ^ rotr32(x, 19) ^ ((x) >> 10))
+#define B2_CH(e, f, g) (((e) & (f)) ^ (~(e) & (g)))
+#define B2_MAJ(a, b, c) (((a) & (b)) ^ ((a) & (c)) ^ ((b) & (c)))
+
+// Round constants: with the 64 rounds fully unrolled these become instruction immediates.
+__device__ constexpr uint32_t kK[64] = {
+    0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+    0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+    0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+    0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+    0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+    0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+    0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+    0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+
+struct Sha256State {
+    uint32_t h[8];
+    __device__ __forceinline__ void init() {
+        h[0] = 0x6a09e667u; h[1] = 0xbb67ae85u; h[2] = 0x3c6ef372u; h[3] = 0xa54ff53au;
+        h[4] = 0x510e527fu; h[5] = 0x9b05688cu; h[6] = 0x1f83d9abu; h[7] = 0x5be0cd19u;
+    }
+};
+
+// One 64-byte block.  w[] holds the 16 big-endian message words and is used as the rolling
+// 16-word window of the message schedule (destroyed).
+__device__ __forceinline__ void sha256_compress(Sha256State &s, uint32_t (&w)[16]) {
+    uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3];
+    uint32_t e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+#pragma unroll
+    for (int t = 0; t < 64; ++t) {
+        if (t >= 16) {
+            w[t & 15] = w[t & 15] + B2_SSIG0(w[(t + 1) & 15]) + w[(t + 9) & 15] + B2_SSIG1(w[(t + 14) & 15]);
+        }
+        const uint32_t t1 = h + B2_BSIG1(e) + B2_CH(e, f, g) + kK[t] + w[t & 15];
+        const uint32_t t2 = B2_BSIG0(a) + B2_MAJ(a, b, c);
+        h = g; g = f; f = e; e = d + t1;
+        d = c; c = b; b = a; a = t1 + t2;
+    }
+    s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d;
+    s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+}
+
+// Final 1-2 blocks: `rem` (< 64) trailing message bytes at `tail`, then 0x80, zeros and the
+// 64-bit big-endian bit length.  Static indexing only (no local memory).
+template <typename ByteLoader>
+__device__ __forceinline__ void sha256_finish(Sha256State &s, ByteLoader load_byte, uint32_t rem,
+                                              uint64_t total_len) {
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t idx = 4 * j + b;
+            uint32_t byte = 0;
+            if (idx < rem) byte = load_byte(idx);
+            else if (idx == rem) byte = 0x80u;
+            v = (v << 8) | byte;
+        }
+        w[j] = v;
+    }
+    const uint64_t bits = total_len << 3;
+    if (rem >= 56) {
+        sha256_compress(s, w);
+#pragma unroll
+        for (int j = 0; j < 14; ++j) w[j] = 0;
+    }
+    w[14] = static_cast<uint32_t>(bits >> 32);
+    w[15] = static_cast<uint32_t>(bits);
+    sha256_compress(s, w);
+}
+
+__device__ __forceinline__ void sha256_store_digest(const Sha256State &s, uint8_t *out) {
+    uint4 lo = make_uint4(bswap32(s.h[0]), bswap32(s.h[1]), bswap32(s.h[2]), bswap32(s.h[3]));
+    uint4 hi = make_uint4(bswap32(s.h[4]), bswap32(s.h[5]), bswap32(s.h[6]), bswap32(s.h[7]));
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        reinterpret_cast<uint4 *>(out)[0] = lo;
+        reinterpret_cast<uint4 *>(out)[1] = hi;
+    } else {
+        const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) out[4 * j + b] = static_cast<uint8_t>(v[j] >> (8 * b));
+    }
+}
+
+__device__ __forceinline__ void words_from_v4(uint32_t (&w)[16], const uint4 (&q)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        w[4 * i + 0] = bswap32(q[i].x); w[4 * i + 1] = bswap32(q[i].y);
+        w[4 * i + 2] = bswap32(q[i].z); w[4 * i + 3] = bswap32(q[i].w);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Path 1: lane streams its own message straight from global memory.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+sha256_lanes_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ offsets,
+                    const uint64_t *__restrict__ lengths, const uint32_t *__restrict__ order,
+                    uint32_t n, uint8_t *__restrict__ digests) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const uint32_t msg = order ? order[slot] : slot;
+    const uint8_t *p = data + offsets[msg];
+    const uint64_t len = lengths[msg];
+    const uint64_t nfull = len >> 6;
+
+    Sha256State s;
+    s.init();
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(p);
+        uint4 cur[4], nxt[4];
+        if (nfull > 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[i] = __ldg(q + i);
+        }
+        for (uint64_t blk = 0; blk < nfull; ++blk) {
+            if (blk + 1 < nfull) {        // prefetch the next block while this one compresses
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nxt[i] = __ldg(q + 4 * (blk + 1) + i);
+            }
+            uint32_t w[16];
+            words_from_v4(w, cur);
+            sha256_compress(s, w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+        }
+    } else {                               // unaligned start: byte loads (correct, slower)
+        for (uint64_t blk = 0; blk < nfull; ++blk) {
+            const uint8_t *b = p + (blk << 6);
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                w[j] = (uint32_t(b[4 * j]) << 24) | (uint32_t(b[4 * j + 1]) << 16) |
+                       (uint32_t(b[4 * j + 2]) << 8) | uint32_t(b[4 * j + 3]);
+            sha256_compress(s, w);
+        }
+    }
+    const uint8_t *tail = p + (nfull << 6);
+    sha256_finish(s, [&](uint32_t i) -> uint32_t { return tail[i]; },
+                  static_cast<uint32_t>(len & 63), len);
+    sha256_store_digest(s, digests + 32ull * msg);
+}
+
+// ----------------------------------------------------------------------------------------
+// Path 2: warp-cooperative staging through shared memory with the bulk-copy (TMA) engine.
+// One warp per CTA-slice owns 32 messages.  Per stage, lane l asks the copy engine for the
+// next kSeg bytes of ITS message into row l of the stage buffer (row pitch kSeg + 16 so that
+// the 32 rows start in different bank groups: LDS.128 by all lanes is conflict-free).  All
+// 32 copies of a stage complete on one mbarrier.  Lanes whose message has fewer than kSeg
+// bytes left request only the remaining whole 16-byte units; the sub-16-byte remainder is
+// read directly from global memory in the padding step.
+// Requires 16-byte aligned message starts (the host packer guarantees it; b2_sha256_batch
+// falls back to path 1 otherwise).
+// ----------------------------------------------------------------------------------------
+constexpr int kSeg = 512;                 // bytes per lane per stage (8 SHA blocks)
+constexpr int kRowPitch = kSeg + 16;
+constexpr int kStages = 2;
+constexpr int kWarpsPerCta = 2;
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+sha256_staged_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ offsets,
+                     const uint64_t *__restrict__ lengths, const uint32_t *__restrict__ order,
+                     uint32_t n, uint8_t *__restrict__ digests) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *wbuf = smem_raw + size_t(warp) * kStages * 32 * kRowPitch;
+    __shared__ __align__(8) uint64_t bars[kWarpsPerCta][kStages];
+
+    const uint32_t slot = (blockIdx.x * kWarpsPerCta + warp) * 32 + lane;
+    const bool live = slot < n;
+    const uint32_t msg = live ? (order ? order[slot] : slot) : 0;
+    const uint8_t *p = live ? data + offsets[msg] : data;
+    const uint64_t len = live ? lengths[msg] : 0;
+    const uint64_t full = len & ~uint64_t(63);          // bytes in full 64-byte blocks
+    // The copy engine needs 16-byte aligned sources; a misaligned message (never produced by
+    // the host packer) skips staging and is hashed with byte loads after the staged loop.
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    const uint64_t body = aligned ? full : 0;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; ++st) mbar_init(&bars[warp][st], 32);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    // number of stages this warp runs = max over lanes of ceil(body / kSeg)
+    uint64_t my_stages = (body + kSeg - 1) / kSeg;
+    uint64_t warp_stages = my_stages;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint64_t other = __shfl_xor_sync(0xffffffffu, warp_stages, o);
+        warp_stages = other > warp_stages ? other : warp_stages;
+    }
+
+    auto issue = [&](uint64_t stage_idx) {
+        const int buf = int(stage_idx % kStages);
+        const uint64_t off = stage_idx * kSeg;
+        uint32_t bytes = 0;
+        if (off < body) bytes = uint32_t(body - off < kSeg ? body - off : kSeg);
+        // every lane arrives once per stage; lanes with data also post their byte count
+        if (bytes) {
+            mbar_arrive_expect_tx(&bars[warp][buf], bytes);
+            bulk_g2s(wbuf + (size_t(buf) * 32 + lane) * kRowPitch, p + off, bytes, &bars[warp][buf]);
+        } else {
+            mbar_arrive(&bars[warp][buf]);
+        }
+    };
+
+    Sha256State s;
+    s.init();
+    for (uint64_t st = 0; st < kStages - 1 && st < warp_stages; ++st) issue(st);
+    for (uint64_t st = 0; st < warp_stages; ++st) {
+        if (st + kStages - 1 < warp_stages) issue(st + kStages - 1);
+        const int buf = int(st % kStages);
+        mbar_wait(&bars[warp][buf], uint32_t((st / kStages) & 1));
+        const uint64_t off = st * kSeg;
+        const uint4 *row = reinterpret_cast<const uint4 *>(wbuf + (size_t(buf) * 32 + lane) * kRowPitch);
+        const int nblk = off < body ? int((body - off < kSeg ? body - off : kSeg) >> 6) : 0;
+        for (int blk = 0; blk < nblk; ++blk) {
+            uint4 q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = row[4 * blk + i];
+            uint32_t w[16];
+            words_from_v4(w, q);
+            sha256_compress(s, w);
+        }
+        __syncwarp();                      // all lanes done with `buf` before it is refilled
+    }
+    if (live) {
+        if (!aligned) {
+            for (uint64_t off = 0; off < full; off += 64) {
+                const uint8_t *b = p + off;
+                uint32_t w[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    w[j] = (uint32_t(b[4 * j]) << 24) | (uint32_t(b[4 * j + 1]) << 16) |
+                           (uint32_t(b[4 * j + 2]) << 8) | uint32_t(b[4 * j + 3]);
+                sha256_compress(s, w);
+            }
+        }
+        const uint8_t *tail = p + full;
+        sha256_finish(s, [&](uint32_t i) -> uint32_t { return tail[i]; },
+                      static_cast<uint32_t>(len & 63), len);
+        sha256_store_digest(s, digests + 32ull * msg);
+    }
+}
+
+__global__ void digest_hex_kernel(const uint8_t *__restrict__ digests, uint32_t n, char *__restrict__ hex) {
+    // one thread per digest byte-pair word: thread t handles 4 digest bytes -> 8 hex chars
+    const uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (t >= uint64_t(n) * 8) return;
+    const uint32_t v = reinterpret_cast<const uint32_t *>(digests)[t];
+    uint32_t out[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const uint32_t byte = (v >> (8 * (2 * half + b))) & 0xff;
+            const uint32_t hi = byte >> 4, lo = byte & 15;
+            const uint32_t chi = hi < 10 ? '0' + hi : 'a' + hi - 10;
+            const uint32_t clo = lo < 10 ? '0' + lo : 'a' + lo - 10;
+            packed |= (chi | (clo << 8)) << (16 * b);
+        }
+        out[half] = packed;
+    }
+    reinterpret_cast<uint2 *>(hex)[t] = make_uint2(out[0], out[1]);
+}
+
+}  // namespace b2
+
+// Path selection: 0 = auto, 1 = force lanes, 2 = force staged (B2_SHA_PATH, read per call;
+// used by the benchmarks to compare the two kernels).
+static int sha_path_override() {
+    const char *e = getenv("B2_SHA_PATH");
+    return e ? atoi(e) : 0;
+}
+
+extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,
+                               const uint64_t *d_lengths, const uint32_t *d_order, uint32_t n,
+                               uint8_t *d_digests, void *stream) {
+    using namespace b2;
+    if (n == 0) return B2_OK;
+    B2_REQUIRE(d_data && d_offsets && d_lengths && d_digests, "b2_sha256_batch: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int path = sha_path_override();
+    if (path == 2) {
+        // staged path needs 16-byte aligned message starts; the caller asserts that by forcing it
+        B2_REQUIRE((reinterpret_cast<uintptr_t>(d_data) & 15) == 0, "staged path: d_data not 16-byte aligned");
+        const size_t smem = size_t(kWarpsPerCta) * kStages * 32 * kRowPitch;
+        static bool attr_set = false;
+        if (!attr_set) {
+            B2_CUDA_CHECK(cudaFuncSetAttribute(sha256_staged_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            attr_set = true;
+        }
+        const uint32_t warps = (n + 31) / 32;
+        const uint32_t grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
+        sha256_staged_kernel<<<grid, 32 * kWarpsPerCta, smem, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests);
+        B2_LAUNCH_CHECK("sha256_staged_kernel");
+        return B2_OK;
+    }
+    // Spread warps over SM sub-partitions: small batches use one warp per CTA so the block
+    // scheduler places consecutive warps on different SMs.
+    const uint32_t warps = (n + 31) / 32;
+    const int block = warps <= uint32_t(sm_count()) * 16u ? 32 : 128;
+    const uint32_t grid = (n + block - 1) / block;
+    sha256_lanes_kernel<<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests);
+    B2_LAUNCH_CHECK("sha256_lanes_kernel");
+    return B2_OK;
+}
+
+extern "C" int b2_digest_hex(const uint8_t *d_digests, uint32_t n, char *d_hex, void *stream) {
+    using namespace b2;
+    if (n == 0) return B2_OK;
+    B2_REQUIRE(d_digests && d_hex, "b2_digest_hex: null pointer");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(d_digests) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_hex) & 7) == 0,
+               "b2_digest_hex: digests must be 4-byte and hex 8-byte aligned");
+    const uint64_t threads = uint64_t(n) * 8;
+    digest_hex_kernel<<<unsigned((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_digests, n, d_hex);
+    B2_LAUNCH_CHECK("digest_hex_kernel");
+    return B2_OK;
+}

@@ -1,0 +1,153 @@
+/*
+ * b2ingest.h — C ABI of libb2ingest.so: the B200 (sm_100a) ingest + label-aggregation
+ * hot path of Elmer-Carvalho/Image-Classification-System, re-built from scratch.
+ *
+ * Conventions
+ *   - Every entry point returns int: 0 = B2_OK, < 0 = b2_status error.  The message of the
+ *     last error on the calling thread is b2_last_error().  No C++ exception crosses the ABI.
+ *   - Pointers named d_* are DEVICE pointers on the current CUDA device of the calling
+ *     thread (in Python: tensor.data_ptr()); h_* are host pointers.  The library never
+ *     frees or retains caller memory; outputs are caller-allocated.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  All
+ *     work is enqueued on it and the call returns without synchronising unless stated.
+ *   - Re-entrant: no global mutable state except immutable per-shape coefficient tables
+ *     owned by b2_resize_plan objects.  Several host threads may call concurrently (the
+ *     reference reaches this path from up to five service threads).
+ *   - There is no CPU fallback.  Without a Blackwell GPU every compute entry point fails.
+ *
+ * Each entry point cites the reference interface (file:line under the reference repo) it
+ * replaces or — where the reference has no implementation — the BASELINE.json config that
+ * requires it.
+ */
+#ifndef B2INGEST_H
+#define B2INGEST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b2_status {
+    B2_OK = 0,
+    B2_ERR_BAD_ARG = -1,      /* null pointer, zero/oversized dimension, misaligned buffer   */
+    B2_ERR_CUDA = -2,         /* a CUDA runtime call failed; see b2_last_error()              */
+    B2_ERR_NOT_SORTED = -3,   /* b2_label_tally(B2_TALLY_SORTED) met rows out of image order  */
+    B2_ERR_NO_DEVICE = -4,    /* no CUDA device / not compute capability 10.x                */
+    B2_ERR_WORKSPACE = -5     /* workspace smaller than the matching *_workspace_bytes()      */
+} b2_status;
+
+/* ---- library ------------------------------------------------------------------------- */
+int b2_version(void);                       /* ABI version, currently 1                       */
+const char *b2_last_error(void);            /* thread-local, never NULL                        */
+int b2_init(int device);                    /* cudaSetDevice + capability check (sm_100)       */
+int b2_device_sm_count(int device, int *sm_count);
+
+/* ---- a1: content hash -------------------------------------------------------------------
+ * Replaces hashlib.sha256(data).hexdigest() at app/services/webdav_sync.py:59 (called :445),
+ * app/services/activity_api_sync.py:798 and app/api/routes/images.py:62, for a batch.
+ * Message i is the byte range d_data[d_offsets[i] .. d_offsets[i] + d_lengths[i]).
+ * One lane hashes one message; a warp owns 32 consecutive slots of `d_order` (a
+ * permutation of 0..n-1, normally messages sorted by length so a warp's lanes finish
+ * together; NULL = identity).  Message starts that are 16-byte aligned take the
+ * 128-bit-load path.  d_digests receives n x 32 raw digest bytes (FIPS 180-4 byte order).
+ */
+int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets, const uint64_t *d_lengths,
+                    const uint32_t *d_order, uint32_t n, uint8_t *d_digests, void *stream);
+
+/* 32-byte digests -> 64 lowercase ASCII hex chars each (the String(64) primary key,
+ * app/db/models.py:212).  d_hex receives n x 64 chars, no terminator. */
+int b2_digest_hex(const uint8_t *d_digests, uint32_t n, char *d_hex, void *stream);
+
+/* ---- a4: dedupe decision ----------------------------------------------------------------
+ * Replaces the sequential lookup-then-insert loop of WebDAVSync._process_image_batch,
+ * app/services/webdav_sync.py:311-400 (lookup :324, insert+flush :329-354, update
+ * :371-398, counters :354/:398/:400), for a batch of n digests:
+ *   d_valid[i] == 0 (or NULL = all valid) marks an image skipped before the lookup
+ *       (:314 invalid, :320 failed download): not counted, is_new = 0, first_index = -1.
+ *   d_existing: m digests already in table `imagens`, sorted ascending in memcmp order
+ *       (NULL/0 = empty table).
+ *   d_seq (NULL = i): arrival order; "first occurrence" = smallest seq (multi-GPU callers
+ *       pass the global image index after the all-gather).
+ * Outputs: d_is_new[i] = 1 iff i is the first valid occurrence of its digest and the digest
+ * is not in d_existing (the insert branch); d_first_index[i] / d_last_index[i] (may be NULL)
+ * = batch index of the first / last valid occurrence of the same digest (identity columns
+ * come from the first, nome_img/caminho_img from the last); d_counts[3] =
+ * {processed, created, updated}.  d_workspace: b2_dedupe_workspace_bytes(n) bytes.
+ */
+uint64_t b2_dedupe_workspace_bytes(uint32_t n);
+int b2_dedupe(const uint8_t *d_digests, const uint8_t *d_valid, const uint32_t *d_seq, uint32_t n,
+              const uint8_t *d_existing, uint64_t m,
+              uint8_t *d_is_new, int32_t *d_first_index, int32_t *d_last_index,
+              uint32_t *d_counts, void *d_workspace, uint64_t workspace_bytes, void *stream);
+
+/* Lookup only (app/api/routes/images.py:65: PK lookup per uploaded file):
+ * d_found_index[i] = position of digest i in the sorted d_existing, or -1. */
+int b2_lookup_sorted(const uint8_t *d_digests, uint32_t n, const uint8_t *d_existing, uint64_t m,
+                     int64_t *d_found_index, void *stream);
+
+/* ---- a12: thumbnail / preview tensor ------------------------------------------------------
+ * Absent in the reference; required by BASELINE.json configs 1,2,3,5 ("hash + 256x256
+ * thumbnail").  Semantics = Pillow (the reference's pinned image library,
+ * requirements.txt:9): Image.resize((out_w,out_h), Image.BILINEAR) on decoded RGB HWC
+ * uint8, bit-exact (two-pass, uint8 intermediate, 22-bit fixed-point taps), plus an
+ * optional float32 CHW preview ((u8/255 - mean[c]) * inv_std[c]).
+ * A plan holds the per-axis tap tables for one (in_h, in_w) -> (out_h, out_w) shape.
+ */
+typedef struct b2_resize_plan b2_resize_plan;
+int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b2_resize_plan **plan);
+int b2_resize_plan_destroy(b2_resize_plan *plan);
+/* Host copies of the tap tables (for tests): bounds = out x {first, count}; coeffs = out x ksize. */
+int b2_resize_plan_taps(const b2_resize_plan *plan, int axis /*0=horizontal,1=vertical*/,
+                        int *ksize, int32_t *h_bounds, int32_t *h_coeffs, uint64_t coeffs_capacity);
+/* Image i of the call starts at d_rgb + d_offsets[i] (HWC, row pitch in_w*3, no padding) and
+ * its outputs go to slot s = d_out_slot ? d_out_slot[i] : i :
+ *   d_thumb   + s * out_h*out_w*3   (uint8 HWC)
+ *   d_preview + s * 3*out_h*out_w   (float32 CHW; NULL = skip). */
+int b2_resize_normalize_batch(const b2_resize_plan *plan, const uint8_t *d_rgb,
+                              const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,
+                              uint8_t *d_thumb, float *d_preview,
+                              const float mean[3], const float inv_std[3], void *stream);
+
+/* ---- a13: per-image label tally + Fleiss partials ---------------------------------------
+ * Absent in the reference (it only groups one user's rows, app/crud/classificacao_crud.py:
+ * 318-322); required by BASELINE.json configs 1,4,5.  Rows are SoA (image_idx int32,
+ * class_idx uint8, active uint8 — the dictionary-encoded `classificacoes` columns id_img,
+ * id_opc, ativo, app/db/models.py:224-241).  Only rows with active != 0 count
+ * (classificacao_crud.py:314).  This shard owns images [image_base, image_base+n_images).
+ *   flags & B2_TALLY_SORTED: rows are ordered by image_idx (an index scan on id_img); the
+ *       kernel builds each 256-image tile in shared memory and writes d_counts with plain
+ *       coalesced stores (d_counts need not be zeroed).  Returns B2_ERR_NOT_SORTED after
+ *       synchronising the stream if a row is found outside its tile.
+ *   otherwise: any order; d_counts is zeroed then built with global atomics.
+ * d_counts: int32[n_images * k].  d_partials: int64[k + B2_PARTIALS_EXTRA] =
+ *   { T_0..T_{k-1}, S2 = sum n_ij^2, R = sum n_i, images with n_i >= 1, images with
+ *     n_i >= 2, sum n_i (n_i - 1), error flag }, ZEROED by the call and accumulated with
+ *   integer atomics — exact, so kappa derived from them is identical on 1/2/4/8 GPUs after
+ *   an integer all-reduce.
+ */
+#define B2_TALLY_SORTED 1u
+#define B2_PARTIALS_EXTRA 6
+uint64_t b2_label_tally_workspace_bytes(uint32_t n_images);
+int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
+                   uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
+                   int32_t *d_counts, int64_t *d_partials,
+                   void *d_workspace, uint64_t workspace_bytes, void *stream);
+/* Partials from an existing count matrix (e.g. after a row-sharded all-reduce of counts).
+ * d_sum_pi (may be NULL): sum over images with n_i >= 2 of (sum_j n_ij^2 - n_i)/(n_i(n_i-1)),
+ * float64, reduced in a fixed order (deterministic for a given n_images). */
+int b2_fleiss_partials(const int32_t *d_counts, uint32_t n_images, uint32_t k,
+                       int64_t *d_partials, double *d_sum_pi, void *stream);
+
+/* ---- next row (f3): per-user aggregation ---------------------------------------------------
+ * Bulk form of COUNT(DISTINCT id_img) WHERE id_con = ? AND ativo
+ * (app/api/routes/classificacoes.py:224-230) for every annotator at once: rows sorted by
+ * (annotator_idx, image_idx); d_distinct[a] = number of distinct images with an active row. */
+int b2_distinct_images_per_annotator(const int32_t *d_annotator_idx, const int32_t *d_image_idx,
+                                     const uint8_t *d_active, uint64_t rows, uint32_t n_annotators,
+                                     uint32_t *d_distinct, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2INGEST_H */
