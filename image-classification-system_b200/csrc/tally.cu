@@ -1,0 +1,540 @@
+// Per-image label tally + integer Fleiss partials for sm_100a.
+//
+// The reference only groups ONE user's active rows by image
+// (app/crud/classificacao_crud.py:318-322) and counts a user's distinct images
+// (app/api/routes/classificacoes.py:224-230); BASELINE.json configs 1,4,5 additionally require
+// the cross-annotator tally and Fleiss' kappa.  Rows are the dictionary-encoded columns of
+// table `classificacoes` (app/db/models.py:224-241): image_idx int32 (id_img), class_idx uint8
+// (id_opc), active uint8 (ativo); only rows with active != 0 count (classificacao_crud.py:314).
+//
+// tally_sorted_kernel — rows ordered by image_idx (an index scan on id_img).  HBM-bound:
+//   6 B read per row + 4*k B written per image, every byte touched once.
+//   * Persistent CTAs.  CTA b nominally owns rows [b*R/G, (b+1)*R/G); so that every image is
+//     written by exactly one CTA with plain stores, the boundary is moved to the next image
+//     change: CTA b owns images [I_b, I_{b+1}), I_b = image_idx[b*R/G] + 1.  It starts
+//     streaming at its nominal row and simply ignores rows of foreign images, so no search
+//     and no pre-pass is needed.
+//   * A thread loads 16 consecutive rows with six 128-bit loads (4 x int4 image_idx, 1 x uint4
+//     class, 1 x uint4 active); a warp covers 512 consecutive rows, a CTA 8192.  The next
+//     block is prefetched into registers while the current one is tallied.
+//   * The CTA keeps a TILE x k int32 count tile in shared memory and tallies with shared-memory
+//     atomics.  Lanes are 16 rows apart, which spreads a warp over several images and keeps
+//     same-address conflicts low even when one class dominates an image.
+//   * When the stream leaves the tile, the tile is written to d_counts with coalesced stores
+//     (d_counts need not be zeroed) and reduced on the fly into the integer partials:
+//     class totals (64-bit shared accumulators), S2 = sum n_ij^2, R = sum n_i, images with
+//     n_i >= 1 / >= 2, sum n_i (n_i - 1).  Partials leave the CTA as 64-bit integer atomics, so
+//     they are exact and independent of scheduling and of the GPU count.
+//   * Every adjacent row pair is checked for order and every row for range; violations are
+//     reported in the partials (unsorted pairs; rows_seen != rows) — the host wrapper turns them
+//     into B2_ERR_NOT_SORTED / B2_ERR_BAD_ARG without the library having to synchronise.
+//
+// tally_scatter_kernel — any row order: global RED.ADD into a zeroed count matrix (bound by L2
+//   atomic throughput, not HBM), followed by the partials pass below.
+//
+// fleiss_partials_kernel — partials (and the float64 sum of P_i for the general-n kappa) from an
+//   existing count matrix, staged through the same shared-memory tile code.
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int kTallyThreads = 512;
+constexpr int kRowsPerThread = 16;
+constexpr int kBlockRows = kTallyThreads * kRowsPerThread;      // 8192
+constexpr int kTileBudgetBytes = 100 * 1024;                    // two CTAs per SM
+constexpr int kMaxTileImages = 512;
+
+// indices into d_partials after the k class totals
+enum { P_S2 = 0, P_R = 1, P_RATED = 2, P_PAIR_IMAGES = 3, P_PAIRS = 4, P_ROWS_SEEN = 5, P_UNSORTED = 6 };
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// CTA-level partial sums live in shared memory (s_part[7], 64-bit): threads fold their
+// contribution in with one shared atomic per warp, so nothing stays in registers between flushes.
+__device__ __forceinline__ void part_add(unsigned long long *s_part, int which, unsigned long long v) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_part[which], v);
+}
+
+// Add the CTA's partials to global memory (integer atomics: exact, order-independent).
+__device__ void commit_partials(const unsigned long long *s_part, const unsigned long long *s_class_tot, uint32_t k,
+                                unsigned long long *g_partials) {
+    if (threadIdx.x < 7 && s_part[threadIdx.x]) atomicAdd(&g_partials[k + threadIdx.x], s_part[threadIdx.x]);
+    for (uint32_t c = threadIdx.x; c < k; c += blockDim.x)
+        if (s_class_tot[c]) atomicAdd(&g_partials[c], s_class_tot[c]);
+}
+
+// Write `n_img` images of the shared tile to global memory and fold them into the partials.
+// Pass 1 (element order, coalesced stores): class totals + S2.  Pass 2 (one thread per image):
+// n_i and the quantities derived from it.  Leaves the tile zeroed.  Caller syncs before and after.
+template <bool kStore, bool kSumPi>
+__device__ __noinline__ void flush_tile(int32_t *tile, uint32_t n_img, uint32_t k, int32_t *g_counts,
+                                        unsigned long long *s_class_tot, unsigned long long *s_part, double *sum_pi) {
+    const uint32_t elems = n_img * k;
+    uint32_t c = threadIdx.x % k;
+    const uint32_t cstep = blockDim.x % k;
+    unsigned long long s2_all = 0;
+    for (uint32_t e = threadIdx.x; e < elems; e += blockDim.x) {
+        const int32_t v = tile[e];
+        if (kStore) g_counts[e] = v;
+        if (v) {
+            s2_all += (unsigned long long)(uint32_t)v * (uint32_t)v;
+            atomicAdd(&s_class_tot[c], (unsigned long long)(uint32_t)v);
+        }
+        c += cstep;
+        if (c >= k) c -= k;
+    }
+    unsigned long long r = 0, pairs = 0, rated = 0, pair_images = 0;
+    for (uint32_t i = threadIdx.x; i < n_img; i += blockDim.x) {
+        const int32_t *row = tile + i * k;
+        unsigned long long n = 0, s2 = 0;
+        for (uint32_t j = 0; j < k; ++j) {
+            const uint32_t v = uint32_t(row[j]);
+            n += v;
+            if (kSumPi) s2 += (unsigned long long)v * v;
+        }
+        r += n;
+        rated += n >= 1;
+        pair_images += n >= 2;
+        pairs += n * (n - (n > 0));
+        if (kSumPi && n >= 2) *sum_pi += double(s2 - n) / double(n * (n - 1));
+    }
+    part_add(s_part, P_S2, s2_all);
+    part_add(s_part, P_R, r);
+    part_add(s_part, P_RATED, rated);
+    part_add(s_part, P_PAIR_IMAGES, pair_images);
+    part_add(s_part, P_PAIRS, pairs);
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < elems; e += blockDim.x) tile[e] = 0;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
+struct RowBlock {
+    int4 idx[4];
+    uint4 cls, act;
+};
+
+__device__ __forceinline__ void load_rows(RowBlock &rb, const int32_t *image_idx, const uint8_t *class_idx,
+                                          const uint8_t *active, uint64_t row0, uint64_t rows) {
+    if (row0 + kRowsPerThread <= rows) {
+        const int4 *pi = reinterpret_cast<const int4 *>(image_idx + row0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rb.idx[j] = __ldg(pi + j);
+        rb.cls = __ldg(reinterpret_cast<const uint4 *>(class_idx + row0));
+        rb.act = __ldg(reinterpret_cast<const uint4 *>(active + row0));
+    } else {                                  // ragged end of the table (or past it): scalar loads
+        int32_t ii[16];
+        uint32_t cw[4] = {0, 0, 0, 0}, aw[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint64_t r = row0 + j;
+            ii[j] = INT32_MIN;                // never inside any image range
+            if (r < rows) {
+                ii[j] = image_idx[r];
+                cw[j >> 2] |= uint32_t(class_idx[r]) << (8 * (j & 3));
+                aw[j >> 2] |= uint32_t(active[r]) << (8 * (j & 3));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rb.idx[j] = make_int4(ii[4 * j], ii[4 * j + 1], ii[4 * j + 2], ii[4 * j + 3]);
+        rb.cls = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+        rb.act = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+    }
+}
+
+struct TallySmem {
+    int32_t *tile;                        // tile_images * k
+    unsigned long long *class_tot;        // k
+    unsigned long long *part;             // 8 (7 used)
+    double *dred;                         // blockDim (fleiss_partials_kernel only)
+};
+__device__ __forceinline__ TallySmem carve_smem(uint8_t *raw, uint32_t tile_images, uint32_t k) {
+    TallySmem s;
+    s.tile = reinterpret_cast<int32_t *>(raw);
+    const size_t tile_bytes = (size_t(tile_images) * k * 4 + 7) & ~size_t(7);
+    s.class_tot = reinterpret_cast<unsigned long long *>(raw + tile_bytes);
+    s.part = s.class_tot + k;
+    s.dred = reinterpret_cast<double *>(s.part + 8);
+    return s;
+}
+
+__global__ void __launch_bounds__(kTallyThreads, 2)
+tally_sorted_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
+                    const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
+                    uint32_t k, uint32_t tile_images, int32_t *__restrict__ counts,
+                    unsigned long long *__restrict__ g_partials) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const TallySmem sm = carve_smem(smem_raw, tile_images, k);
+    int32_t *tile = sm.tile;
+
+    const uint32_t G = gridDim.x, b = blockIdx.x;
+    const int32_t img_end_all = image_base + int32_t(n_images);                  // host checked: fits int32
+    // nominal row range, aligned to the 16-row vector granule
+    const uint64_t nom0 = ((rows / G) * b + (rows % G) * b / G) & ~uint64_t(kRowsPerThread - 1);
+    const uint64_t nom1 = b + 1 == G ? rows : (((rows / G) * (b + 1) + (rows % G) * (b + 1) / G) & ~uint64_t(kRowsPerThread - 1));
+    // owned image range [I0, I1): the image under the nominal boundary row belongs to the CTA before
+    auto boundary = [&](uint64_t nom) -> int32_t {
+        const int32_t v = image_idx[nom];
+        return v < image_base ? image_base : (v >= img_end_all - 1 ? img_end_all : v + 1);
+    };
+    int32_t I0, I1;
+    if (rows == 0) {                                                             // nothing to stream: split the zero fill
+        I0 = image_base + int32_t(uint64_t(n_images) * b / G);
+        I1 = image_base + int32_t(uint64_t(n_images) * (b + 1) / G);
+    } else {
+        I0 = b == 0 ? image_base : boundary(nom0);
+        I1 = b + 1 == G ? img_end_all : boundary(nom1);
+        if (I1 < I0) I1 = I0;                                                    // unsorted input: own nothing
+    }
+
+    for (uint32_t e = threadIdx.x; e < tile_images * k; e += blockDim.x) tile[e] = 0;
+    for (uint32_t c = threadIdx.x; c < k + 8; c += blockDim.x) sm.class_tot[c] = 0;   // class totals + partials
+    __syncthreads();
+
+    int32_t base = I0;                                                           // first image of the tile
+    int32_t tile_end = I1 - base > int32_t(tile_images) ? base + int32_t(tile_images) : I1;
+    uint32_t rows_seen = 0, unsorted = 0;
+
+    auto flush = [&]() {                                                         // uniform
+        __syncthreads();
+        flush_tile<true, false>(tile, uint32_t(tile_end - base), k,
+                                counts + size_t(base - image_base) * k, sm.class_tot, sm.part, nullptr);
+        base = tile_end;
+        tile_end = I1 - base > int32_t(tile_images) ? base + int32_t(tile_images) : I1;
+        __syncthreads();
+    };
+
+    RowBlock cur;
+    uint64_t blk = nom0;
+    while (blk < rows) {
+        const uint64_t row0 = blk + uint64_t(threadIdx.x) * kRowsPerThread;
+        const uint64_t nblk = blk + kBlockRows;
+        load_rows(cur, image_idx, class_idx, active, row0, rows);
+        {   // pull the next block into L2 while this one is tallied (no registers held)
+            const uint64_t nrow0 = row0 + kBlockRows;
+            if (nrow0 < rows) {
+                prefetch_l2(image_idx + nrow0);
+                if ((threadIdx.x & 7) == 0) {                                     // one 128-byte line per 8 threads
+                    prefetch_l2(class_idx + nrow0);
+                    prefetch_l2(active + nrow0);
+                }
+            }
+        }
+
+        const int32_t ii[16] = {cur.idx[0].x, cur.idx[0].y, cur.idx[0].z, cur.idx[0].w, cur.idx[1].x, cur.idx[1].y,
+                                cur.idx[1].z, cur.idx[1].w, cur.idx[2].x, cur.idx[2].y, cur.idx[2].z, cur.idx[2].w,
+                                cur.idx[3].x, cur.idx[3].y, cur.idx[3].z, cur.idx[3].w};
+        const uint32_t cw[4] = {cur.cls.x, cur.cls.y, cur.cls.z, cur.cls.w};
+        const uint32_t aw[4] = {cur.act.x, cur.act.y, cur.act.z, cur.act.w};
+
+        // order check of every adjacent pair this CTA is responsible for: pairs (r-1, r) with
+        // nom0 <= r < nom1 (nom1 is a multiple of 16 or the table end, so a thread is all in or out)
+        if (row0 < nom1) {
+            int32_t prev = row0 > 0 ? __ldg(image_idx + row0 - 1) : INT32_MIN;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                unsorted += (ii[j] < prev) & (ii[j] != INT32_MIN);               // INT32_MIN = past the table
+                prev = ii[j];
+            }
+        }
+
+        bool any_mine = false;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) any_mine |= (ii[j] < I1) & (ii[j] != INT32_MIN);
+        for (;;) {
+            // Tile-relative counter index of each of my rows (kNoKey: not in this tile / bad class /
+            // inactive).  A thread's 16 rows are consecutive, so most share the image and its dominant
+            // class: rows equal to the first key are merged into ONE shared atomic, which removes most
+            // same-address conflicts between the lanes of a warp.
+            constexpr uint32_t kNoKey = 0xffffffffu;
+            bool beyond_tile = false;
+            auto key_of = [&](int j) -> uint32_t {
+                const int32_t img = ii[j];
+                const uint32_t c = (cw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                const uint32_t a = (aw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                const bool in_tile = (img >= base) & (img < tile_end) & (c < k);
+                return (in_tile && a) ? uint32_t(img - base) * k + c : kNoKey;
+            };
+            const uint32_t k0 = key_of(0);
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int32_t img = ii[j];
+                const uint32_t c = (cw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                rows_seen += (img >= base) & (img < tile_end) & (c < k);
+                beyond_tile |= (img >= tile_end) & (img < I1);
+                m += key_of(j) == k0;
+            }
+            if (k0 != kNoKey) atomicAdd(&tile[k0], int32_t(m));
+#pragma unroll
+            for (int j = 1; j < 16; ++j) {
+                const uint32_t kj = key_of(j);
+                if (kj != k0 && kj != kNoKey) atomicAdd(&tile[kj], 1);
+            }
+            if (!__syncthreads_or(beyond_tile)) break;
+            flush();                                                             // tile complete: write it, open the next
+        }
+        // the stream has left this CTA's images once a whole block past the nominal end is foreign
+        const bool stream_live = __syncthreads_or(any_mine) || nblk < nom1;
+        if (!stream_live) break;
+        blk = nblk;
+    }
+    // remaining tiles (the open one and any image range without rows)
+    while (base < I1) flush();
+    part_add(sm.part, P_ROWS_SEEN, rows_seen);
+    part_add(sm.part, P_UNSORTED, unsorted);
+    __syncthreads();
+    commit_partials(sm.part, sm.class_tot, k, g_partials);
+}
+
+// Any row order: one RED.ADD per active row into a zeroed count matrix.
+__global__ void __launch_bounds__(256)
+tally_scatter_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
+                     const uint8_t *__restrict__ active, uint64_t rows, int64_t image_base, uint32_t n_images,
+                     uint32_t k, int32_t *__restrict__ counts, unsigned long long *__restrict__ g_partials) {
+    unsigned long long seen = 0;
+    const uint64_t groups = (rows + kRowsPerThread - 1) / kRowsPerThread;
+    for (uint64_t g = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; g < groups; g += uint64_t(gridDim.x) * blockDim.x) {
+        RowBlock rb;
+        load_rows(rb, image_idx, class_idx, active, g * kRowsPerThread, rows);
+        const int32_t ii[16] = {rb.idx[0].x, rb.idx[0].y, rb.idx[0].z, rb.idx[0].w, rb.idx[1].x, rb.idx[1].y,
+                                rb.idx[1].z, rb.idx[1].w, rb.idx[2].x, rb.idx[2].y, rb.idx[2].z, rb.idx[2].w,
+                                rb.idx[3].x, rb.idx[3].y, rb.idx[3].z, rb.idx[3].w};
+        const uint32_t cw[4] = {rb.cls.x, rb.cls.y, rb.cls.z, rb.cls.w};
+        const uint32_t aw[4] = {rb.act.x, rb.act.y, rb.act.z, rb.act.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int64_t rel = int64_t(ii[j]) - image_base;
+            const uint32_t c = (cw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            const uint32_t a = (aw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            if (rel >= 0 && rel < int64_t(n_images) && c < k && ii[j] != INT32_MIN) {
+                ++seen;
+                if (a) atomicAdd(&counts[size_t(rel) * k + c], 1);
+            }
+        }
+    }
+    seen = warp_sum(seen);
+    if ((threadIdx.x & 31) == 0 && seen) atomicAdd(&g_partials[k + P_ROWS_SEEN], seen);
+}
+
+// Partials from a count matrix.  Grid size is a function of n_images only, block sums are
+// combined in block order by the last CTA to finish: sum_pi is reproducible for a given shape.
+__global__ void __launch_bounds__(kTallyThreads, 2)
+fleiss_partials_kernel(const int32_t *__restrict__ counts, uint32_t n_images, uint32_t k, uint32_t tile_images,
+                       unsigned long long *__restrict__ g_partials, double *__restrict__ sum_pi_out,
+                       double *__restrict__ block_sums, unsigned int *__restrict__ ticket) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const TallySmem sm = carve_smem(smem_raw, tile_images, k);
+    int32_t *tile = sm.tile;
+    double *s_dred = sm.dred;
+
+    for (uint32_t c = threadIdx.x; c < k + 8; c += blockDim.x) sm.class_tot[c] = 0;
+    double my_pi = 0.0;
+    const uint32_t n_tiles = (n_images + tile_images - 1) / tile_images;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t i0 = t * tile_images;
+        const uint32_t n_img = min(tile_images, n_images - i0);
+        const int32_t *src = counts + size_t(i0) * k;
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < n_img * k; e += blockDim.x) tile[e] = __ldg(src + e);
+        __syncthreads();
+        if (sum_pi_out) flush_tile<false, true>(tile, n_img, k, nullptr, sm.class_tot, sm.part, &my_pi);
+        else flush_tile<false, false>(tile, n_img, k, nullptr, sm.class_tot, sm.part, nullptr);
+    }
+    __syncthreads();
+    commit_partials(sm.part, sm.class_tot, k, g_partials);
+    if (sum_pi_out) {
+        s_dred[threadIdx.x] = my_pi;
+        __syncthreads();
+        for (int s = blockDim.x >> 1; s > 0; s >>= 1) {                          // fixed-order tree
+            if (int(threadIdx.x) < s) s_dred[threadIdx.x] += s_dred[threadIdx.x + s];
+            __syncthreads();
+        }
+        __shared__ bool last;
+        if (threadIdx.x == 0) {
+            block_sums[blockIdx.x] = s_dred[0];
+            __threadfence();
+            last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (last && threadIdx.x == 0) {
+            __threadfence();
+            double s = 0.0;
+            for (uint32_t i = 0; i < gridDim.x; ++i) s += reinterpret_cast<volatile double *>(block_sums)[i];
+            *sum_pi_out = s;
+        }
+    }
+}
+
+static uint32_t pick_tile_images(uint32_t k) {
+    uint32_t t = kTileBudgetBytes / (4u * k);
+    if (t > uint32_t(kMaxTileImages)) t = kMaxTileImages;
+    if (t >= 32) t &= ~31u;
+    return t < 1 ? 1 : t;
+}
+static size_t tally_smem_bytes(uint32_t tile_images, uint32_t k) {
+    size_t tile = (size_t(tile_images) * k * 4 + 7) & ~size_t(7);
+    return tile + size_t(k) * 8 + 8 * 8 + size_t(kTallyThreads) * 8;
+}
+constexpr uint32_t kFleissGridMax = 592;
+
+static cudaError_t ensure_smem(const void *fn, size_t bytes) {
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+}
+
+}  // namespace b2
+
+extern "C" uint64_t b2_label_tally_workspace_bytes(uint32_t n_images) {
+    (void)n_images;
+    return 0;
+}
+
+extern "C" uint64_t b2_fleiss_workspace_bytes(uint32_t n_images) {
+    (void)n_images;
+    return 16 + 8ull * b2::kFleissGridMax;
+}
+
+extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
+                              uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
+                              int32_t *d_counts, int64_t *d_partials, void *d_workspace,
+                              uint64_t workspace_bytes, void *stream) {
+    using namespace b2;
+    (void)d_workspace; (void)workspace_bytes;
+    B2_REQUIRE(d_counts && d_partials, "b2_label_tally: null output pointer");
+    B2_REQUIRE(k >= 1 && k <= 256, "b2_label_tally: k must be in 1..256 (class_idx is uint8)");
+    B2_REQUIRE(n_images >= 1 && uint64_t(n_images) * k < (1ull << 40), "b2_label_tally: n_images out of range");
+    B2_REQUIRE(uint64_t(image_base) + n_images <= 0x7fffffffull, "b2_label_tally: image range exceeds int32");
+    B2_REQUIRE(rows == 0 || (d_image_idx && d_class_idx && d_active), "b2_label_tally: null row pointer");
+    B2_REQUIRE(((reinterpret_cast<uintptr_t>(d_image_idx) | reinterpret_cast<uintptr_t>(d_class_idx) |
+                 reinterpret_cast<uintptr_t>(d_active)) & 15) == 0, "b2_label_tally: row arrays must be 16-byte aligned");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(d_partials) & 7) == 0 && (reinterpret_cast<uintptr_t>(d_counts) & 3) == 0,
+               "b2_label_tally: misaligned output");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long *partials = reinterpret_cast<unsigned long long *>(d_partials);
+    B2_CUDA_CHECK(cudaMemsetAsync(partials, 0, (size_t(k) + B2_PARTIALS_EXTRA) * 8, st));
+    const uint32_t tile_images = pick_tile_images(k);
+    const size_t smem = tally_smem_bytes(tile_images, k);
+    if (flags & B2_TALLY_SORTED) {
+        B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_sorted_kernel), smem));
+        uint64_t want = (rows + 4ull * kBlockRows - 1) / (4ull * kBlockRows);
+        const uint64_t by_images = (uint64_t(n_images) + tile_images - 1) / tile_images;
+        if (want < by_images) want = by_images;      // image ranges without rows still get written in parallel
+        const uint64_t cap = 2ull * uint64_t(sm_count());
+        uint32_t grid = uint32_t(want < 1 ? 1 : (want > cap ? cap : want));
+        if (rows < uint64_t(grid) * kRowsPerThread) grid = 1;   // nominal ranges must be distinct multiples of 16 rows
+        tally_sorted_kernel<<<grid, kTallyThreads, smem, st>>>(d_image_idx, d_class_idx, d_active, rows,
+                                                               int32_t(image_base), n_images, k, tile_images,
+                                                               d_counts, partials);
+        B2_LAUNCH_CHECK("tally_sorted_kernel");
+        return B2_OK;
+    }
+    B2_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, size_t(n_images) * k * 4, st));
+    if (rows) {
+        const uint64_t groups = (rows + kRowsPerThread - 1) / kRowsPerThread;
+        uint64_t grid = (groups + 255) / 256;
+        const uint64_t cap = 8ull * uint64_t(sm_count());
+        if (grid > cap) grid = cap;
+        tally_scatter_kernel<<<unsigned(grid), 256, 0, st>>>(d_image_idx, d_class_idx, d_active, rows,
+                                                            int64_t(image_base), n_images, k, d_counts, partials);
+        B2_LAUNCH_CHECK("tally_scatter_kernel");
+    }
+    B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(fleiss_partials_kernel), smem));
+    const uint32_t n_tiles = (n_images + tile_images - 1) / tile_images;
+    const uint32_t grid = n_tiles < kFleissGridMax ? n_tiles : kFleissGridMax;
+    fleiss_partials_kernel<<<grid, kTallyThreads, smem, st>>>(d_counts, n_images, k, tile_images, partials,
+                                                             nullptr, nullptr, nullptr);
+    B2_LAUNCH_CHECK("fleiss_partials_kernel");
+    return B2_OK;
+}
+
+extern "C" int b2_fleiss_partials(const int32_t *d_counts, uint32_t n_images, uint32_t k, int64_t *d_partials,
+                                  double *d_sum_pi, void *d_workspace, uint64_t workspace_bytes, void *stream) {
+    using namespace b2;
+    B2_REQUIRE(d_counts && d_partials, "b2_fleiss_partials: null pointer");
+    B2_REQUIRE(k >= 1 && k <= 256 && n_images >= 1, "b2_fleiss_partials: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long *partials = reinterpret_cast<unsigned long long *>(d_partials);
+    B2_CUDA_CHECK(cudaMemsetAsync(partials, 0, (size_t(k) + B2_PARTIALS_EXTRA) * 8, st));
+    const uint32_t tile_images = pick_tile_images(k);
+    const size_t smem = tally_smem_bytes(tile_images, k);
+    B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(fleiss_partials_kernel), smem));
+    const uint32_t n_tiles = (n_images + tile_images - 1) / tile_images;
+    const uint32_t grid = n_tiles < kFleissGridMax ? n_tiles : kFleissGridMax;
+    double *block_sums = nullptr;
+    unsigned int *ticket = nullptr;
+    if (d_sum_pi) {
+        B2_REQUIRE(d_workspace && (reinterpret_cast<uintptr_t>(d_workspace) & 7) == 0,
+                   "b2_fleiss_partials: d_sum_pi needs an 8-byte aligned workspace");
+        if (workspace_bytes < b2_fleiss_workspace_bytes(n_images))
+            return fail(B2_ERR_WORKSPACE, "b2_fleiss_partials: workspace %llu < required %llu bytes",
+                        (unsigned long long)workspace_bytes, (unsigned long long)b2_fleiss_workspace_bytes(n_images));
+        ticket = static_cast<unsigned int *>(d_workspace);
+        block_sums = reinterpret_cast<double *>(static_cast<uint8_t *>(d_workspace) + 16);
+        B2_CUDA_CHECK(cudaMemsetAsync(ticket, 0, 16, st));
+    }
+    fleiss_partials_kernel<<<grid, kTallyThreads, smem, st>>>(d_counts, n_images, k, tile_images, partials,
+                                                             d_sum_pi, block_sums, ticket);
+    B2_LAUNCH_CHECK("fleiss_partials_kernel");
+    return B2_OK;
+}
+
+// Host-side verdict on a tally's partials (copied to the host by the caller).
+extern "C" int b2_label_tally_status(const int64_t *h_partials, uint32_t k, uint64_t rows) {
+    using namespace b2;
+    B2_REQUIRE(h_partials != nullptr, "b2_label_tally_status: null pointer");
+    if (h_partials[k + P_UNSORTED] != 0)
+        return fail(B2_ERR_NOT_SORTED, "label tally: %lld adjacent row pairs are out of image order (B2_TALLY_SORTED)",
+                    (long long)h_partials[k + P_UNSORTED]);
+    if (uint64_t(h_partials[k + P_ROWS_SEEN]) != rows)
+        return fail(B2_ERR_BAD_ARG, "label tally: %llu of %llu rows tallied; the rest have image_idx or class_idx out of range",
+                    (unsigned long long)h_partials[k + P_ROWS_SEEN], (unsigned long long)rows);
+    return B2_OK;
+}
+
+// Bulk COUNT(DISTINCT id_img) WHERE id_con = ? AND ativo (app/api/routes/classificacoes.py:224-230)
+// for every annotator at once.  Rows sorted by (annotator_idx, image_idx): an active row opens a
+// new distinct image iff no earlier active row of the same annotator has the same image.
+namespace b2 {
+__global__ void __launch_bounds__(256)
+distinct_images_kernel(const int32_t *__restrict__ annotator_idx, const int32_t *__restrict__ image_idx,
+                       const uint8_t *__restrict__ active, uint64_t rows, uint32_t n_annotators,
+                       uint32_t *__restrict__ distinct) {
+    for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < rows; r += uint64_t(gridDim.x) * blockDim.x) {
+        if (!active[r]) continue;
+        const int32_t a = annotator_idx[r], img = image_idx[r];
+        if (a < 0 || uint32_t(a) >= n_annotators) continue;
+        // walk back over the rows of the same (annotator, image) run looking for an earlier active one
+        bool first = true;
+        for (uint64_t q = r; q-- > 0;) {
+            if (annotator_idx[q] != a || image_idx[q] != img) break;
+            if (active[q]) { first = false; break; }
+        }
+        if (first) atomicAdd(&distinct[a], 1u);
+    }
+}
+}  // namespace b2
+
+extern "C" int b2_distinct_images_per_annotator(const int32_t *d_annotator_idx, const int32_t *d_image_idx,
+                                                const uint8_t *d_active, uint64_t rows, uint32_t n_annotators,
+                                                uint32_t *d_distinct, void *stream) {
+    using namespace b2;
+    B2_REQUIRE(d_distinct != nullptr && n_annotators >= 1, "b2_distinct_images_per_annotator: bad output");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B2_CUDA_CHECK(cudaMemsetAsync(d_distinct, 0, size_t(n_annotators) * 4, st));
+    if (rows == 0) return B2_OK;
+    B2_REQUIRE(d_annotator_idx && d_image_idx && d_active, "b2_distinct_images_per_annotator: null pointer");
+    uint64_t grid = (rows + 255) / 256;
+    const uint64_t cap = 16ull * uint64_t(sm_count());
+    if (grid > cap) grid = cap;
+    distinct_images_kernel<<<unsigned(grid), 256, 0, st>>>(d_annotator_idx, d_image_idx, d_active, rows,
+                                                          n_annotators, d_distinct);
+    B2_LAUNCH_CHECK("distinct_images_kernel");
+    return B2_OK;
+}

@@ -1,0 +1,120 @@
+"""Label aggregation: cross-annotator per-image tally + Fleiss' kappa, and the bulk form of the
+reference's per-user counts.
+
+The reference aggregates only per user (app/crud/classificacao_crud.py:284-324,
+app/api/routes/classificacoes.py:224-230); BASELINE.json configs 1,4,5 require the
+cross-annotator tally and kappa.  Rows are the dictionary-encoded columns of table
+``classificacoes`` (app/db/models.py:224-241): ``image_idx`` int32 (id_img), ``class_idx``
+uint8 (id_opc), ``active`` uint8 (ativo).  Only active rows count (classificacao_crud.py:314).
+
+kappa is computed on the host in float64 from INTEGER partials produced on the device, so it is
+bit-identical for any number of GPUs once the partials are all-reduced (dist.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import engine
+
+
+@dataclass
+class TallyResult:
+    counts: np.ndarray            # int32 [n_images, k]
+    class_totals: np.ndarray      # int64 [k]
+    S2: int                       # sum n_ij^2
+    R: int                        # sum n_i  (active rows tallied)
+    n_rated: int                  # images with n_i >= 1
+    n_pairs_images: int           # images with n_i >= 2
+    pairs: int                    # sum n_i (n_i - 1)
+
+    def kappa(self, n_images: int, n_raters: int) -> float:
+        return fleiss_kappa(self.class_totals, self.S2, self.R, n_images, n_raters)
+
+
+def fleiss_kappa(class_totals: Sequence[int], S2: int, R: int, n_images: int, n_raters: int) -> float:
+    """Classical Fleiss kappa, constant ``n_raters`` ratings per image:
+    P_bar = (S2 - R) / (N n (n - 1));  P_e = sum_j (T_j / R)^2;  kappa = (P_bar - P_e) / (1 - P_e)."""
+    p_bar = float(int(S2) - int(R)) / float(int(n_images) * int(n_raters) * (int(n_raters) - 1))
+    pj = np.asarray(class_totals, dtype=np.float64) / float(int(R))
+    p_e = float(np.sum(pj * pj))
+    return (p_bar - p_e) / (1.0 - p_e)
+
+
+def fleiss_kappa_general(class_totals: Sequence[int], R: int, sum_pi: float, n_pairs_images: int) -> float:
+    """Variable ratings per image: P_bar = mean of P_i over images with n_i >= 2 (``sum_pi`` from
+    :func:`engine.fleiss_partials_device`), P_e from the class totals of all ratings."""
+    p_bar = float(sum_pi) / float(n_pairs_images)
+    pj = np.asarray(class_totals, dtype=np.float64) / float(int(R))
+    p_e = float(np.sum(pj * pj))
+    return (p_bar - p_e) / (1.0 - p_e)
+
+
+def _rows_to_device(image_idx, class_idx, active, device):
+    dev = torch.device("cuda", engine.init(device))
+
+    def up(a, dt):
+        if isinstance(a, torch.Tensor):
+            return a.to(dev, dtype=dt, non_blocking=True).contiguous()
+        arr = np.ascontiguousarray(a, dtype={torch.int32: np.int32, torch.uint8: np.uint8}[dt])
+        return torch.from_numpy(arr).to(dev, non_blocking=True)
+
+    return up(image_idx, torch.int32), up(class_idx, torch.uint8), up(active, torch.uint8)
+
+
+def label_tally(image_idx, class_idx, active, n_images: int, k: int, sorted_by_image: Optional[bool] = None,
+                image_base: int = 0, device: Optional[int] = None) -> TallyResult:
+    """Tally host (NumPy) or device rows.  ``sorted_by_image=None`` checks the order on the host
+    for NumPy input (cheap) and assumes clustered input for device tensors."""
+    if active is None:
+        active = np.ones(len(image_idx), dtype=np.uint8)
+    if sorted_by_image is None:
+        if isinstance(image_idx, np.ndarray):
+            sorted_by_image = bool(np.all(image_idx[1:] >= image_idx[:-1])) if image_idx.size else True
+        else:
+            sorted_by_image = True
+    d_img, d_cls, d_act = _rows_to_device(image_idx, class_idx, active, device)
+    counts, partials = engine.label_tally_device(d_img, d_cls, d_act, n_images, k, image_base, sorted_by_image)
+    p = partials.cpu().numpy()
+    engine.check_tally(p, k, d_img.numel())
+    d = engine.partials_dict(p, k)
+    return TallyResult(counts=counts.cpu().numpy(), class_totals=d["class_totals"], S2=d["S2"], R=d["R"],
+                       n_rated=d["n_rated"], n_pairs_images=d["n_pairs_images"], pairs=d["pairs"])
+
+
+def distinct_images_per_annotator(annotator_idx, image_idx, active, n_annotators: int,
+                                  device: Optional[int] = None) -> np.ndarray:
+    """Bulk ``COUNT(DISTINCT id_img) WHERE id_con = ? AND ativo`` (routes/classificacoes.py:
+    224-230) for every annotator; rows in any order (sorted here by (annotator, image))."""
+    a = np.ascontiguousarray(annotator_idx, dtype=np.int32)
+    i = np.ascontiguousarray(image_idx, dtype=np.int32)
+    act = np.ascontiguousarray(active, dtype=np.uint8)
+    order = np.lexsort((i, a))
+    dev = torch.device("cuda", engine.init(device))
+    out = engine.distinct_images_per_annotator_device(
+        torch.from_numpy(a[order]).to(dev), torch.from_numpy(i[order]).to(dev),
+        torch.from_numpy(act[order]).to(dev), n_annotators)
+    return out.cpu().numpy()
+
+
+class LabelEncoder:
+    """Dictionary encoder for ``classificacoes`` rows: id_img
+    (char64) -> dense image index, id_opc (UUID) -> class index, ativo -> uint8."""
+
+    def __init__(self, image_hashes: Sequence[str], option_ids: Sequence[str]):
+        self.image_index: Dict[str, int] = {h: i for i, h in enumerate(image_hashes)}
+        self.class_index: Dict[str, int] = {str(o): j for j, o in enumerate(option_ids)}
+        if len(self.class_index) > 256:
+            raise ValueError("class_idx is uint8: at most 256 options per environment")
+
+    def encode(self, rows: Sequence[Dict]):
+        """rows: dicts with id_img, id_opc, ativo.  Returns SoA arrays sorted by image index."""
+        n = len(rows)
+        img = np.fromiter((self.image_index[r["id_img"]] for r in rows), dtype=np.int32, count=n)
+        cls = np.fromiter((self.class_index[str(r["id_opc"])] for r in rows), dtype=np.uint8, count=n)
+        act = np.fromiter((1 if r["ativo"] is True else 0 for r in rows), dtype=np.uint8, count=n)
+        order = np.argsort(img, kind="stable")
+        return img[order], cls[order], act[order]

@@ -1,0 +1,183 @@
+"""Drop-in for the ingest hot path of ``app/services/webdav_sync.py`` (reference).
+
+Same class name, method names, argument meaning, return types and error behaviour as the
+reference's ``WebDAVSync`` for the methods ON the path:
+
+  _calculate_hash_from_bytes(data) -> str                  webdav_sync.py:49-59
+  _validate_image(file_info) -> bool                       webdav_sync.py:61-81
+  _get_image_metadata(image_data) -> Dict                  webdav_sync.py:83-103  (host, Pillow header)
+  _download_and_process_image(image_info) -> (hash, meta)  webdav_sync.py:428-465
+  _process_image_batch(images, folder_path, conjunto_id)   webdav_sync.py:296-426
+  sync_images_in_folder(folder_path, conjunto_id)          webdav_sync.py:247-294 (batch loop only)
+
+What changes is the shape of the work: the reference hashes, looks up and inserts one image at
+a time; here a batch is downloaded first, hashed in ONE device call (libb2ingest
+``b2_sha256_batch``), resolved against the table with ONE ``IN`` lookup plus the device dedupe
+kernel (``b2_dedupe``), and then applied in arrival order.  Results — hashes, created/updated
+decisions, the stats dict and the final rows — are identical to the sequential reference
+(tests/test_services_gpu.py replays tests/golden/reference_ingest.json).
+
+``db`` is an :class:`..store.ImageStore` (the storage engine is out of scope; INTEGRATION.md
+shows the SQLAlchemy adapter).  Listing folders, marking removed images and folder bookkeeping
+(:105-245, :467-532) stay in the reference.
+"""
+from __future__ import annotations
+
+import io
+import logging
+from datetime import datetime, timezone
+from typing import Callable, Dict, List, Optional, Tuple
+
+from .. import engine
+from ..ingest import hash_and_dedupe
+
+logger = logging.getLogger(__name__)
+
+NEXTCLOUD_SYNC_BATCH_SIZE = 50        # app/core/config.py:56
+
+
+def _utc_now() -> datetime:
+    return datetime.now(timezone.utc)
+
+
+class WebDAVSync:
+    """Batch-on-device version of the reference's full-scan ingest."""
+
+    ALLOWED_MIME_TYPES = [
+        "image/jpeg", "image/jpg", "image/png", "image/gif", "image/bmp", "image/tiff", "image/webp",
+    ]
+    ALLOWED_EXTENSIONS = [".jpg", ".jpeg", ".png", ".gif", ".bmp", ".tiff", ".webp"]
+    SYNC_METHOD = "webdav"
+
+    def __init__(self, nextcloud_client, db, now: Callable[[], datetime] = _utc_now,
+                 batch_size: int = NEXTCLOUD_SYNC_BATCH_SIZE, device: Optional[int] = None):
+        self.client = nextcloud_client
+        self.db = db
+        self._now = now
+        self.batch_size = batch_size
+        self.device = device
+
+    # ------------------------------------------------------------------ single-item API
+    def _calculate_hash_from_bytes(self, data: bytes) -> str:
+        """SHA-256 of the file bytes, lowercase hex (64 chars): a 1-element device batch."""
+        return engine.hash_batch([data], self.device)[0]
+
+    def _validate_image(self, file_info: Dict) -> bool:
+        name = file_info.get("name", "").lower()
+        if not any(name.endswith(ext) for ext in self.ALLOWED_EXTENSIONS):
+            return False
+        content_type = file_info.get("content_type", "").lower()
+        return any(mime in content_type for mime in self.ALLOWED_MIME_TYPES)
+
+    def _get_image_metadata(self, image_data: bytes) -> Dict:
+        """Header parse only, in the reference's own host library (Pillow); ``{}`` on any error."""
+        try:
+            from PIL import Image as PILImage
+
+            img = PILImage.open(io.BytesIO(image_data))
+            return {"width": img.width, "height": img.height, "format": img.format, "mode": img.mode}
+        except Exception as e:  # noqa: BLE001 - the reference swallows everything here
+            logger.warning("metadata extraction failed: %s", e)
+            return {}
+
+    def _fetch(self, image_info: Dict) -> Optional[bytes]:
+        """Download into memory; ``None`` on any failure (never aborts the batch)."""
+        try:
+            return self.client.get_file(image_info.get("path", "")).content
+        except Exception as e:  # noqa: BLE001 - connection error, timeout, anything: skip the image
+            logger.warning("download failed for %s: %s", image_info.get("name", "unknown"), e)
+            return None
+
+    def _download_and_process_image(self, image_info: Dict) -> Tuple[Optional[str], Dict]:
+        data = self._fetch(image_info)
+        if data is None:
+            return None, {}
+        try:
+            return self._calculate_hash_from_bytes(data), self._get_image_metadata(data)
+        except Exception as e:  # noqa: BLE001
+            logger.debug("processing failed for %s: %s", image_info.get("name", "unknown"), e)
+            return None, {}
+
+    # ------------------------------------------------------------------ batch API
+    @staticmethod
+    def _nextcloud_meta(info: Dict, full: bool) -> Dict:
+        lm = info.get("last_modified")
+        meta = {
+            "file_id": info.get("file_id", ""),
+            "etag": info.get("etag", ""),
+            "last_modified": lm.isoformat() if lm else None,
+        }
+        if full:
+            meta["content_type"] = info.get("content_type", "")
+            meta["size"] = info.get("content_length", 0)
+        return meta
+
+    def _process_image_batch(self, images: List[Dict], folder_path: str, conjunto_id) -> Dict[str, int]:
+        now = self._now()
+        datas: List[Optional[bytes]] = [
+            self._fetch(info) if self._validate_image(info) else None for info in images
+        ]
+        try:
+            decision = hash_and_dedupe(datas, existing_hashes=lambda hs: self.db.get_many(hs).keys(),
+                                       device=self.device)
+        except Exception as e:  # noqa: BLE001 - device failure: nothing of the batch is processed
+            logger.error("device ingest failed for batch in %s: %s", folder_path, e)
+            return {"processed": 0, "created": 0, "updated": 0}
+
+        for i, info in enumerate(images):
+            content_hash = decision.hashes[i]
+            if not content_hash:
+                continue
+            if decision.is_new[i]:
+                nc = self._nextcloud_meta(info, full=True)
+                self.db.insert({
+                    "content_hash": content_hash,
+                    "nome_img": info.get("name", ""),
+                    "caminho_img": info.get("path", ""),
+                    "metadados": {
+                        "nextcloud": {"file_id": nc["file_id"], "etag": nc["etag"],
+                                      "content_type": nc["content_type"], "size": nc["size"],
+                                      "last_modified": nc["last_modified"]},
+                        "image": self._get_image_metadata(datas[i]),
+                        "sync": {"sync_method": self.SYNC_METHOD, "sync_timestamp": now.isoformat()},
+                    },
+                    "existe_no_nextcloud": True,
+                    "data_proc": now,
+                    "data_sinc": now,
+                    "id_cnj": conjunto_id,
+                })
+            else:
+                row = self.db.get(content_hash)
+                md = row.get("metadados")
+                if md:
+                    if "nextcloud" in md:
+                        md["nextcloud"].update(self._nextcloud_meta(info, full=False))
+                    else:
+                        md["nextcloud"] = self._nextcloud_meta(info, full=True)
+                    md["sync"] = {"sync_method": self.SYNC_METHOD, "sync_timestamp": now.isoformat()}
+                self.db.update(content_hash, {
+                    "nome_img": info.get("name", ""),
+                    "caminho_img": info.get("path", ""),
+                    "existe_no_nextcloud": True,
+                    "data_sinc": now,
+                    "metadados": md,
+                })
+        return dict(decision.stats)
+
+    def sync_images_in_folder(self, folder_path: str, conjunto_id) -> Dict[str, int]:
+        """The batch loop of the reference (:273-283).  Marking removed images (:286) is
+        bookkeeping outside the hot path: ``images_marked_removed`` stays 0 here."""
+        stats = {"images_processed": 0, "images_created": 0, "images_updated": 0, "images_marked_removed": 0}
+        try:
+            items = self.client.list_folder(folder_path, depth=1)
+            images = self.client.filter_images(items)
+            for i in range(0, len(images), self.batch_size):
+                b = self._process_image_batch(images[i:i + self.batch_size], folder_path, conjunto_id)
+                stats["images_processed"] += b["processed"]
+                stats["images_created"] += b["created"]
+                stats["images_updated"] += b["updated"]
+                self.db.commit()
+        except Exception:
+            self.db.rollback()
+            raise
+        return stats

@@ -32,7 +32,7 @@ typedef enum b2_status {
     B2_OK = 0,
     B2_ERR_BAD_ARG = -1,      /* null pointer, zero/oversized dimension, misaligned buffer   */
     B2_ERR_CUDA = -2,         /* a CUDA runtime call failed; see b2_last_error()              */
-    B2_ERR_NOT_SORTED = -3,   /* b2_label_tally(B2_TALLY_SORTED) met rows out of image order  */
+    B2_ERR_NOT_SORTED = -3,   /* b2_label_tally_status: rows out of image order in sorted mode */
     B2_ERR_NO_DEVICE = -4,    /* no CUDA device / not compute capability 10.x                */
     B2_ERR_WORKSPACE = -5     /* workspace smaller than the matching *_workspace_bytes()      */
 } b2_status;
@@ -115,29 +115,37 @@ int b2_resize_normalize_batch(const b2_resize_plan *plan, const uint8_t *d_rgb,
  * class_idx uint8, active uint8 — the dictionary-encoded `classificacoes` columns id_img,
  * id_opc, ativo, app/db/models.py:224-241).  Only rows with active != 0 count
  * (classificacao_crud.py:314).  This shard owns images [image_base, image_base+n_images).
- *   flags & B2_TALLY_SORTED: rows are ordered by image_idx (an index scan on id_img); the
- *       kernel builds each 256-image tile in shared memory and writes d_counts with plain
- *       coalesced stores (d_counts need not be zeroed).  Returns B2_ERR_NOT_SORTED after
- *       synchronising the stream if a row is found outside its tile.
+ *   flags & B2_TALLY_SORTED: rows are ordered by image_idx (an index scan on id_img); each
+ *       CTA builds tiles of images in shared memory and writes d_counts with plain coalesced
+ *       stores (d_counts need not be zeroed).
  *   otherwise: any order; d_counts is zeroed then built with global atomics.
  * d_counts: int32[n_images * k].  d_partials: int64[k + B2_PARTIALS_EXTRA] =
  *   { T_0..T_{k-1}, S2 = sum n_ij^2, R = sum n_i, images with n_i >= 1, images with
- *     n_i >= 2, sum n_i (n_i - 1), error flag }, ZEROED by the call and accumulated with
- *   integer atomics — exact, so kappa derived from them is identical on 1/2/4/8 GPUs after
- *   an integer all-reduce.
+ *     n_i >= 2, sum n_i (n_i - 1), rows tallied (active or not, image and class in range),
+ *     adjacent row pairs out of image order (sorted mode only) },
+ *   ZEROED by the call and accumulated with integer atomics — exact, so kappa derived from
+ *   them is identical on 1/2/4/8 GPUs after an integer all-reduce.
+ * The call never synchronises.  Once the partials are on the host, b2_label_tally_status()
+ * turns the last two entries into B2_OK / B2_ERR_NOT_SORTED / B2_ERR_BAD_ARG (a row with
+ * image_idx or class_idx out of range); on error d_counts is unspecified.
+ * Row arrays must be 16-byte aligned.  No workspace is needed (pass NULL, 0).
  */
 #define B2_TALLY_SORTED 1u
-#define B2_PARTIALS_EXTRA 6
+#define B2_PARTIALS_EXTRA 7
 uint64_t b2_label_tally_workspace_bytes(uint32_t n_images);
 int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
                    uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
                    int32_t *d_counts, int64_t *d_partials,
                    void *d_workspace, uint64_t workspace_bytes, void *stream);
-/* Partials from an existing count matrix (e.g. after a row-sharded all-reduce of counts).
- * d_sum_pi (may be NULL): sum over images with n_i >= 2 of (sum_j n_ij^2 - n_i)/(n_i(n_i-1)),
- * float64, reduced in a fixed order (deterministic for a given n_images). */
+int b2_label_tally_status(const int64_t *h_partials, uint32_t k, uint64_t rows);   /* host only */
+/* Partials from an existing count matrix (e.g. after a row-sharded all-reduce of counts); the
+ * last two entries stay 0.  d_sum_pi (may be NULL): sum over images with n_i >= 2 of
+ * (sum_j n_ij^2 - n_i)/(n_i(n_i-1)), float64, reduced in a fixed order (reproducible for a given
+ * n_images, k); needs b2_fleiss_workspace_bytes() of 8-byte aligned workspace. */
+uint64_t b2_fleiss_workspace_bytes(uint32_t n_images);
 int b2_fleiss_partials(const int32_t *d_counts, uint32_t n_images, uint32_t k,
-                       int64_t *d_partials, double *d_sum_pi, void *stream);
+                       int64_t *d_partials, double *d_sum_pi,
+                       void *d_workspace, uint64_t workspace_bytes, void *stream);
 
 /* ---- next row (f3): per-user aggregation ---------------------------------------------------
  * Bulk form of COUNT(DISTINCT id_img) WHERE id_con = ? AND ativo

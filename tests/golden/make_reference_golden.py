@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import asyncio
 import base64
+import copy
 import io
 import json
 import os
@@ -312,8 +313,8 @@ def dump_imagens(session, models):
             "caminho_img": r.caminho_img,
             "existe_no_nextcloud": r.existe_no_nextcloud,
             "id_cnj": str(r.id_cnj),
-            "image_meta": md.get("image"),
-            "nextcloud_meta": md.get("nextcloud"),
+            "image_meta": copy.deepcopy(md.get("image")),          # snapshot: later batches mutate these dicts
+            "nextcloud_meta": copy.deepcopy(md.get("nextcloud")),
             "sync_method": (md.get("sync") or {}).get("sync_method"),
             "first_seen": r.data_proc == r.data_sinc,
         }

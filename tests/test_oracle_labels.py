@@ -1,0 +1,80 @@
+"""Oracle pinning, labels: per-user paths against the reference's own outputs; tally + kappa
+against the published Fleiss (1971) example (parity unpinned by the reference: it has no
+tally and no kappa)."""
+import uuid
+
+import numpy as np
+
+from oracle import (classification_delta, distinct_image_count, fleiss_kappa, fleiss_kappa_general,
+                    fleiss_partials, group_by_image, history_grouping, label_tally, synth_label_rows)
+
+
+def _rows(ref_labels):
+    return [dict(r, id_con=uuid.UUID(r["id_con"])) for r in ref_labels["classificacoes"]]
+
+
+def test_group_by_image(ref_labels):
+    rows = _rows(ref_labels)
+    for case in ref_labels["group_by_image"]:
+        try:
+            u = uuid.UUID(case["id_con"])
+        except ValueError:
+            assert case["result"] == {}
+            continue
+        got = group_by_image(rows, u, case["images"])
+        assert {h: [c["id_cla"] for c in lst] for h, lst in got.items()} == case["result"]
+
+
+def test_distinct_count(ref_labels):
+    rows = _rows(ref_labels)
+    for case in ref_labels["distinct_count"]:
+        if case["id_con"] is None:
+            assert case["total"] == 0
+        else:
+            assert distinct_image_count(rows, uuid.UUID(case["id_con"])) == case["total"]
+
+
+def test_history_grouping(ref_labels):
+    got = history_grouping([tuple(j) for j in ref_labels["history"]["joined"]])
+    want = ref_labels["history"]["items"]
+    assert len(got) == len(want)
+    # reference quirk: "total" is query.count() = joined ROWS of the page query, not grouped items
+    assert ref_labels["history"]["total"] == len(ref_labels["history"]["joined"])
+    for g, w in zip(got, want):
+        assert g["content_hash"] == w["content_hash"]
+        assert g["ids_opcoes"] == w["ids_opcoes"]
+        assert g["opcao_escolhida"] == w["opcao_escolhida"]
+
+
+def test_classification_delta(ref_labels):
+    for d in ref_labels["delta"]:
+        inativar, criar, reativar, novas, inc = classification_delta(
+            d["before_active"], d["before_inactive"], d["wanted"])
+        assert novas == d["total_novas"]
+        assert int(inc) == d["counter_delta"]
+        after_active = (set(d["before_active"]) - inativar) | criar | reativar
+        assert sorted(after_active) == d["after_active"]
+
+
+def test_fleiss_1971(fleiss71):
+    counts = np.array(fleiss71["table"], dtype=np.int32)
+    p = fleiss_partials(counts)
+    n, N = fleiss71["n_raters"], counts.shape[0]
+    assert p["R"] == n * N
+    kappa = fleiss_kappa(p["class_totals"], p["S2"], p["R"], N, n)
+    assert round(kappa, 3) == fleiss71["kappa"]
+    assert abs(fleiss_kappa_general(counts) - kappa) < 1e-12
+    p_bar = (p["S2"] - p["R"]) / (N * n * (n - 1))
+    assert round(p_bar, 3) == fleiss71["P_bar"]
+
+
+def test_tally_matches_naive_loop():
+    img, cls, act = synth_label_rows(50, 7, 9)
+    counts = label_tally(img, cls, act, 50, 7)
+    naive = np.zeros((50, 7), dtype=np.int32)
+    for i, c, a in zip(img, cls, act):
+        if a:
+            naive[i, c] += 1
+    assert np.array_equal(counts, naive)
+    p = fleiss_partials(counts)
+    assert p["R"] == int(act.sum()) and p["S2"] == int((naive.astype(np.int64) ** 2).sum())

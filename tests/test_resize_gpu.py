@@ -1,0 +1,96 @@
+"""Parity, thumbnail / preview (parity unpinned by the reference: it has no resize; oracle =
+Pillow, its pinned image library).  north_star tolerance: +-1 LSB for uint8, 1e-5 relative for
+float32 — the kernels reproduce Pillow's integer arithmetic, so the tests assert the stronger
+bit-exact result and state the tolerance they would fall back to."""
+import numpy as np
+import pytest
+import torch
+
+from ics_b200 import engine
+from oracle import precompute_coeffs, preview_f32, synth_image, thumbnail_u8
+
+pytestmark = pytest.mark.gpu
+
+U8_TOL = 0          # contract: <= 1 LSB; achieved: identical
+F32_RTOL = 1e-5
+
+
+def _check(imgs, out_h, out_w, mean=(0, 0, 0), inv_std=(1, 1, 1)):
+    thumb, prev = engine.thumbnails(imgs, out_h, out_w, True, mean, inv_std)
+    for i, im in enumerate(imgs):
+        want = thumbnail_u8(im, out_h, out_w)
+        diff = np.abs(thumb[i].astype(np.int16) - want.astype(np.int16))
+        assert diff.max(initial=0) <= U8_TOL, (im.shape, int(diff.max()), float((diff > 0).mean()))
+        np.testing.assert_allclose(prev[i], preview_f32(want, mean, inv_std), rtol=F32_RTOL, atol=1e-7)
+
+
+@pytest.fixture(params=["auto", "generic"])
+def resize_path(request, monkeypatch):
+    monkeypatch.setenv("B2_RESIZE_PATH", {"auto": "0", "generic": "1"}[request.param])
+    return request.param
+
+
+def test_committed_pillow_fixtures(pillow_cases, resize_path):
+    for img, want in pillow_cases:
+        thumb, _ = engine.thumbnails([img], want.shape[0], want.shape[1], want_preview=False)
+        assert np.array_equal(thumb[0], want), (img.shape, want.shape)
+
+
+def test_tap_tables_match_pillow_restatement():
+    for (ih, iw) in [(1080, 1920), (512, 512), (2160, 3840), (300, 257), (100, 100)]:
+        plan = engine.ResizePlan(ih, iw, 256, 256)
+        for axis, size in ((0, iw), (1, ih)):
+            b, k, ks = plan.taps(axis)
+            ob, ok, oks = precompute_coeffs(size, 256)
+            assert ks == oks and np.array_equal(b, ob) and np.array_equal(k, ok)
+        plan.close()
+
+
+@pytest.mark.parametrize("shape", [(512, 512), (1080, 1920), (256, 256), (300, 257), (2160, 3840), (97, 1031),
+                                   (128, 96), (4096, 4096)])
+def test_baseline_shapes_to_256(shape, resize_path):
+    if resize_path == "generic" and shape[0] * shape[1] > 1080 * 1920:
+        pytest.skip("generic kernel is the slow fallback; large shapes covered by auto")
+    n = 1 if shape[0] >= 2160 else 2
+    imgs = [synth_image(g, *shape) for g in range(n)]
+    _check(imgs, 256, 256)
+
+
+def test_mixed_shapes_one_call_and_normalisation():
+    imgs = [synth_image(0, 512, 512), synth_image(1, 270, 480), synth_image(2, 512, 512), synth_image(3, 31, 17)]
+    _check(imgs, 256, 256, mean=(0.485, 0.456, 0.406), inv_std=(1 / 0.229, 1 / 0.224, 1 / 0.225))
+
+
+def test_non_square_outputs_and_upscale(resize_path):
+    imgs = [synth_image(4, 200, 300)]
+    _check(imgs, 64, 96)
+    _check(imgs, 256, 128)
+    _check([synth_image(5, 20, 30)], 256, 256)
+
+
+def test_structured_images_extremes():
+    black = np.zeros((1080, 1920, 3), np.uint8)
+    white = np.full((1080, 1920, 3), 255, np.uint8)
+    yy, xx = np.mgrid[0:1080, 0:1920]
+    checker = (((xx // 3 + yy // 5) % 2) * 255).astype(np.uint8)[..., None].repeat(3, 2)
+    _check([black, white, np.ascontiguousarray(checker)], 256, 256)
+
+
+def test_device_batch_full_size_properties():
+    """64 x 1080p on device: duplicates give identical thumbnails; a constant image stays
+    constant; sampled images match Pillow."""
+    n, H, W = 64, 1080, 1920
+    g = torch.Generator(device="cuda").manual_seed(0xB200)
+    data = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda", generator=g)
+    data[7] = data[3]
+    data[9] = 200
+    off = torch.arange(n, dtype=torch.int64, device="cuda") * (H * W * 3)
+    plan = engine.get_plan(H, W, 256, 256)
+    thumb, prev = plan.run(data.view(-1), off)
+    torch.cuda.synchronize()
+    assert torch.equal(thumb[7], thumb[3])
+    assert bool((thumb[9] == 200).all())
+    assert torch.equal(prev[9], torch.full_like(prev[9], float(np.float32(200) * np.float32(1 / 255))))
+    for i in (0, 3, 63):
+        want = thumbnail_u8(data[i].cpu().numpy(), 256, 256)
+        assert np.array_equal(thumb[i].cpu().numpy(), want)
