@@ -51,24 +51,44 @@ struct Sha256State {
     }
 };
 
+// Integer add on the FMA pipe.  ncu on the first version of this kernel (profiles/r1_*): the ALU
+// pipe (SHF/LOP3/IADD3/PRMT, 16 lanes/clk per sub-partition) was 87 % busy and the FMA pipe 4 %.
+// Every rotate and boolean has to stay on the ALU pipe, but an add does not: `mad.lo x, 1, y`
+// is emitted as IMAD.IADD, which issues on the FMA pipe.  V = 0 leaves the choice to ptxas
+// (IADD3 on the ALU pipe), V >= 1 moves all 592 adds of a block.
+template <int V>
+__device__ __forceinline__ uint32_t addp(uint32_t a, uint32_t b, uint32_t one) {
+    if (V == 0) return a + b;
+    // `one` is a kernel argument equal to 1: ptxas cannot fold the multiply away (it turns a literal
+    // `mad x, 1, y` back into IADD3), so this stays an IMAD on the FMA pipe.
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
+
 // One 64-byte block.  w[] holds the 16 big-endian message words and is used as the rolling
 // 16-word window of the message schedule (destroyed).
-__device__ __forceinline__ void sha256_compress(Sha256State &s, uint32_t (&w)[16]) {
+template <int V>
+__device__ __forceinline__ void sha256_compress_v(Sha256State &s, uint32_t (&w)[16], uint32_t one) {
     uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3];
     uint32_t e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
 #pragma unroll
     for (int t = 0; t < 64; ++t) {
         if (t >= 16) {
-            w[t & 15] = w[t & 15] + B2_SSIG0(w[(t + 1) & 15]) + w[(t + 9) & 15] + B2_SSIG1(w[(t + 14) & 15]);
+            w[t & 15] = addp<V>(addp<V>(w[t & 15], B2_SSIG0(w[(t + 1) & 15]), one),
+                                addp<V>(w[(t + 9) & 15], B2_SSIG1(w[(t + 14) & 15]), one), one);
         }
-        const uint32_t t1 = h + B2_BSIG1(e) + B2_CH(e, f, g) + kK[t] + w[t & 15];
-        const uint32_t t2 = B2_BSIG0(a) + B2_MAJ(a, b, c);
-        h = g; g = f; f = e; e = d + t1;
-        d = c; c = b; b = a; a = t1 + t2;
+        // off the critical path: h + K + W (+ d); on it: Sigma1(e) + Ch(e,f,g)
+        const uint32_t hkw = addp<V>(addp<V>(h, kK[t], one), w[t & 15], one);
+        const uint32_t t1 = addp<V>(addp<V>(B2_BSIG1(e), B2_CH(e, f, g), one), hkw, one);
+        const uint32_t t2 = addp<V>(B2_BSIG0(a), B2_MAJ(a, b, c), one);
+        h = g; g = f; f = e; e = addp<V>(d, t1, one);
+        d = c; c = b; b = a; a = addp<V>(t1, t2, one);
     }
     s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d;
     s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
+__device__ __forceinline__ void sha256_compress(Sha256State &s, uint32_t (&w)[16]) { sha256_compress_v<0>(s, w, 1u); }
 
 // Final 1-2 blocks: `rem` (< 64) trailing message bytes at `tail`, then 0x80, zeros and the
 // 64-bit big-endian bit length.  Static indexing only (no local memory).
@@ -126,10 +146,11 @@ __device__ __forceinline__ void words_from_v4(uint32_t (&w)[16], const uint4 (&q
 // ----------------------------------------------------------------------------------------
 // Path 1: lane streams its own message straight from global memory.
 // ----------------------------------------------------------------------------------------
+template <int V>
 __global__ void __launch_bounds__(128)
 sha256_lanes_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ offsets,
                     const uint64_t *__restrict__ lengths, const uint32_t *__restrict__ order,
-                    uint32_t n, uint8_t *__restrict__ digests) {
+                    uint32_t n, uint8_t *__restrict__ digests, uint32_t one) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n) return;
     const uint32_t msg = order ? order[slot] : slot;
@@ -153,7 +174,7 @@ sha256_lanes_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict
             }
             uint32_t w[16];
             words_from_v4(w, cur);
-            sha256_compress(s, w);
+            sha256_compress_v<V>(s, w, one);
 #pragma unroll
             for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
         }
@@ -310,6 +331,12 @@ static int sha_path_override() {
     return e ? atoi(e) : 0;
 }
 
+// B2_SHA_VARIANT: 0 = adds left to ptxas (ALU pipe), 1 = adds forced onto the FMA pipe (default).
+static int sha_variant_override() {
+    const char *e = getenv("B2_SHA_VARIANT");
+    return e ? atoi(e) : 1;
+}
+
 extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,
                                const uint64_t *d_lengths, const uint32_t *d_order, uint32_t n,
                                uint8_t *d_digests, void *stream) {
@@ -339,7 +366,10 @@ extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,
     const uint32_t warps = (n + 31) / 32;
     const int block = warps <= uint32_t(sm_count()) * 16u ? 32 : 128;
     const uint32_t grid = (n + block - 1) / block;
-    sha256_lanes_kernel<<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests);
+    if (sha_variant_override() == 0)
+        sha256_lanes_kernel<0><<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests, 1u);
+    else
+        sha256_lanes_kernel<1><<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests, 1u);
     B2_LAUNCH_CHECK("sha256_lanes_kernel");
     return B2_OK;
 }

@@ -294,6 +294,210 @@ tally_sorted_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__rest
     commit_partials(sm.part, sm.class_tot, k, g_partials);
 }
 
+// ----------------------------------------------------------------------------------------
+// tally_warp_kernel<NG> — the product kernel for rows ordered by image_idx.  No shared-memory
+// atomics at all (measured: ~2 cycles per lane, the bottleneck of the tile kernel above):
+//   * A WARP streams a contiguous row range and owns the images that START in it (same
+//     ownership rule as above, per warp instead of per CTA).
+//   * Lane l owns the counters of classes {l, l+32, ...} of the image being accumulated, in
+//     REGISTERS (NG = ceil(k/32) of them).  A group of 128 rows is loaded as four steps of 32
+//     consecutive rows (coalesced 128-byte / 32-byte requests), the next group is prefetched
+//     into registers.  Per step the class values are bit-sliced with warp ballots (one
+//     ballot per class bit); lane l ANDs the slices that spell its class numbers, masks with
+//     the ballot of "active, in range, same image" and adds the population count.
+//   * When the image changes, each lane stores its counters straight to d_counts — one
+//     coalesced k*4-byte store per image, no tile, no flush — and folds them into its own
+//     class totals / sum of squares.  n_i is the population count of the row mask, uniform
+//     across the warp, so R, rated images and pairs need no reduction at all.
+//   * Partials are combined per CTA in shared memory, then one 64-bit atomic per value and CTA.
+// ----------------------------------------------------------------------------------------
+constexpr int kWarpKernelThreads = 256;
+constexpr int kGroupRows = 128;
+
+template <int NG>
+__global__ void __launch_bounds__(kWarpKernelThreads)
+tally_warp_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
+                  const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
+                  uint32_t k, uint64_t n_workers, int32_t *__restrict__ counts,
+                  unsigned long long *__restrict__ g_partials) {
+    constexpr int NBITS = NG == 1 ? 5 : (NG == 2 ? 6 : (NG == 4 ? 7 : 8));
+    __shared__ unsigned long long s_tot[256 + 8];
+    for (uint32_t i = threadIdx.x; i < 256 + 8; i += blockDim.x) s_tot[i] = 0;
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31;
+    // n_workers warps share the rows; the host keeps it <= rows/128 so that nominal starts are distinct
+    const uint64_t W = n_workers;
+    const uint64_t w = uint64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const bool worker = w < W;
+    const int32_t img_end_all = image_base + int32_t(n_images);
+    auto nominal = [&](uint64_t i) -> uint64_t {
+        return i >= W ? rows : (((rows / W) * i + (rows % W) * i / W) & ~uint64_t(kGroupRows - 1));
+    };
+    const uint64_t nom0 = nominal(w), nom1 = nominal(w + 1);
+    auto boundary = [&](uint64_t nom) -> int32_t {
+        const int32_t v = __ldg(image_idx + nom);
+        return v < image_base ? image_base : (v >= img_end_all - 1 ? img_end_all : v + 1);
+    };
+    int32_t I0, I1;
+    if (!worker) {
+        I0 = I1 = img_end_all;                                // spare warp of the last CTA: owns nothing
+    } else if (rows == 0) {
+        I0 = image_base + int32_t(uint64_t(n_images) * w / W);
+        I1 = image_base + int32_t(uint64_t(n_images) * (w + 1) / W);
+    } else {
+        I0 = w == 0 ? image_base : boundary(nom0);
+        I1 = w + 1 == W ? img_end_all : boundary(nom1);
+        if (I1 < I0) I1 = I0;                                 // unsorted input
+    }
+
+    // inv[b]: all-ones when bit b of this lane's class numbers is 0 (so slice ^ inv selects "bit == mine")
+    uint32_t inv[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) inv[b] = ((lane >> b) & 1u) ? 0u : 0xffffffffu;
+
+    uint32_t cnt[NG];
+    unsigned long long tot[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) { cnt[g] = 0; tot[g] = 0; }
+    unsigned long long s2 = 0, sum_r = 0, pairs = 0;
+    uint32_t rated = 0, pair_images = 0, seen = 0, unsorted = 0, n_cur = 0;
+    int32_t cur = I0;
+
+    // store the finished image, fold it into the partials, zero-fill images without rows up to `next`
+    auto finish_image = [&](int32_t next) {
+        if (cur < I1) {
+            int32_t *dst = counts + size_t(cur - image_base) * k;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const uint32_t c = lane + 32u * g;
+                if (c < k) dst[c] = int32_t(cnt[g]);
+                tot[g] += cnt[g];
+                s2 += (unsigned long long)cnt[g] * cnt[g];
+                cnt[g] = 0;
+            }
+            sum_r += n_cur;
+            rated += n_cur >= 1;
+            pair_images += n_cur >= 2;
+            pairs += (unsigned long long)n_cur * (n_cur - (n_cur > 0));
+            n_cur = 0;
+            const int32_t stop = next < I1 ? next : I1;
+            for (int32_t img = cur + 1; img < stop; ++img) {
+                int32_t *z = counts + size_t(img - image_base) * k;
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                    if (lane + 32u * g < k) z[lane + 32u * g] = 0;
+            }
+        }
+        cur = next;
+    };
+
+    // A group is 128 consecutive rows; in step s lane l holds row grp + 32*s + l, so the rows of a
+    // step are consecutive and (for ordered input) images never go backwards from step to step.
+    struct Group { int32_t idx[4]; uint32_t cls[4], act[4]; };
+    auto load_group = [&](uint64_t grp) -> Group {
+        Group q;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint64_t r = grp + 32ull * s + lane;
+            q.idx[s] = INT32_MAX;                            // past the table: sorts last, owned by nobody
+            q.cls[s] = 0;
+            q.act[s] = 0;
+            if (r < rows) {
+                q.idx[s] = __ldg(image_idx + r);
+                q.cls[s] = __ldg(class_idx + r);
+                q.act[s] = __ldg(active + r);
+            }
+        }
+        return q;
+    };
+
+    if (worker && nom0 < rows) {
+        int32_t carry = nom0 > 0 ? __ldg(image_idx + nom0 - 1) : INT32_MIN;   // last row before the step (order check)
+        Group q = load_group(nom0);
+        for (uint64_t grp = nom0; grp < rows; grp += kGroupRows) {
+            Group nq;
+            const bool has_next = grp + kGroupRows < rows;
+            if (has_next) nq = load_group(grp + kGroupRows);
+
+            bool any_mine = false;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int32_t img = q.idx[s];
+                const uint32_t c = q.cls[s];
+                const bool a = q.act[s] != 0;
+                // order check of the pairs (r-1, r), nom0 <= r < nom1, this warp is responsible for
+                {
+                    int32_t before = __shfl_up_sync(0xffffffffu, img, 1);
+                    if (lane == 0) before = carry;
+                    unsorted += (img < before) & (grp < nom1) & (img != INT32_MAX);
+                    carry = __shfl_sync(0xffffffffu, img, 31);
+                }
+                const bool mine = (img >= I0) & (img < I1);
+                const bool ok = mine & (c < k);
+                seen += ok;
+                any_mine |= img < I1;
+                uint32_t slice[NBITS];
+#pragma unroll
+                for (int b = 0; b < NBITS; ++b) slice[b] = __ballot_sync(0xffffffffu, (c >> b) & 1u);
+                uint32_t low = slice[0] ^ inv[0];
+#pragma unroll
+                for (int b = 1; b < 5; ++b) low &= slice[b] ^ inv[b];
+
+                auto accumulate = [&](uint32_t vm) {          // vm: rows of image `cur` that count
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        uint32_t m = low & vm;
+#pragma unroll
+                        for (int b = 5; b < NBITS; ++b) m &= ((g >> (b - 5)) & 1) ? slice[b] : ~slice[b];
+                        cnt[g] += __popc(m);
+                    }
+                    n_cur += __popc(vm);
+                };
+
+                if (__all_sync(0xffffffffu, mine & (img == cur))) {       // common case: one image, all mine
+                    accumulate(__ballot_sync(0xffffffffu, ok & a));
+                } else {
+                    uint32_t rem = __ballot_sync(0xffffffffu, mine);
+                    while (rem) {
+                        const int first = __ffs(rem) - 1;
+                        const int32_t nxt = __shfl_sync(0xffffffffu, img, first);
+                        if (nxt != cur) finish_image(nxt);
+                        const uint32_t same = __ballot_sync(0xffffffffu, img == nxt) & rem;
+                        accumulate(__ballot_sync(0xffffffffu, ok & a & (img == nxt)));
+                        rem &= ~same;
+                    }
+                }
+            }
+            // past the nominal end and nothing of this group is below I1: the stream has left my images
+            if (grp + kGroupRows >= nom1 && !__any_sync(0xffffffffu, any_mine)) break;
+            q = nq;
+        }
+    }
+    finish_image(I1);
+
+    // ---- commit: warp -> CTA (shared, 64-bit) -> global (one atomic per value and CTA) ----
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+        if (tot[g]) atomicAdd(&s_tot[lane + 32 * g], tot[g]);
+    {
+        const unsigned long long v_s2 = warp_sum(s2), v_seen = warp_sum(seen), v_uns = warp_sum(unsorted);
+        if (lane == 0) {
+            if (v_s2) atomicAdd(&s_tot[256 + P_S2], v_s2);
+            if (sum_r) atomicAdd(&s_tot[256 + P_R], sum_r);
+            if (rated) atomicAdd(&s_tot[256 + P_RATED], (unsigned long long)rated);
+            if (pair_images) atomicAdd(&s_tot[256 + P_PAIR_IMAGES], (unsigned long long)pair_images);
+            if (pairs) atomicAdd(&s_tot[256 + P_PAIRS], pairs);
+            if (v_seen) atomicAdd(&s_tot[256 + P_ROWS_SEEN], v_seen);
+            if (v_uns) atomicAdd(&s_tot[256 + P_UNSORTED], v_uns);
+        }
+    }
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < k; c += blockDim.x)
+        if (s_tot[c]) atomicAdd(&g_partials[c], s_tot[c]);
+    if (threadIdx.x < 7 && s_tot[256 + threadIdx.x]) atomicAdd(&g_partials[k + threadIdx.x], s_tot[256 + threadIdx.x]);
+}
+
 // Any row order: one RED.ADD per active row into a zeroed count matrix.
 __global__ void __launch_bounds__(256)
 tally_scatter_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
@@ -391,6 +595,12 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
 
 }  // namespace b2
 
+// B2_TALLY_PATH: 0 = auto (warp kernel), 1 = shared-memory tile kernel (comparison).
+static int tally_path_override() {
+    const char *e = getenv("B2_TALLY_PATH");
+    return e ? atoi(e) : 0;
+}
+
 extern "C" uint64_t b2_label_tally_workspace_bytes(uint32_t n_images) {
     (void)n_images;
     return 0;
@@ -412,7 +622,7 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
     B2_REQUIRE(n_images >= 1 && uint64_t(n_images) * k < (1ull << 40), "b2_label_tally: n_images out of range");
     B2_REQUIRE(uint64_t(image_base) + n_images <= 0x7fffffffull, "b2_label_tally: image range exceeds int32");
     B2_REQUIRE(rows == 0 || (d_image_idx && d_class_idx && d_active), "b2_label_tally: null row pointer");
-    B2_REQUIRE(((reinterpret_cast<uintptr_t>(d_image_idx) | reinterpret_cast<uintptr_t>(d_class_idx) |
+    B2_REQUIRE(rows == 0 || ((reinterpret_cast<uintptr_t>(d_image_idx) | reinterpret_cast<uintptr_t>(d_class_idx) |
                  reinterpret_cast<uintptr_t>(d_active)) & 15) == 0, "b2_label_tally: row arrays must be 16-byte aligned");
     B2_REQUIRE((reinterpret_cast<uintptr_t>(d_partials) & 7) == 0 && (reinterpret_cast<uintptr_t>(d_counts) & 3) == 0,
                "b2_label_tally: misaligned output");
@@ -422,17 +632,40 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
     const uint32_t tile_images = pick_tile_images(k);
     const size_t smem = tally_smem_bytes(tile_images, k);
     if (flags & B2_TALLY_SORTED) {
-        B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_sorted_kernel), smem));
-        uint64_t want = (rows + 4ull * kBlockRows - 1) / (4ull * kBlockRows);
-        const uint64_t by_images = (uint64_t(n_images) + tile_images - 1) / tile_images;
-        if (want < by_images) want = by_images;      // image ranges without rows still get written in parallel
-        const uint64_t cap = 2ull * uint64_t(sm_count());
-        uint32_t grid = uint32_t(want < 1 ? 1 : (want > cap ? cap : want));
-        if (rows < uint64_t(grid) * kRowsPerThread) grid = 1;   // nominal ranges must be distinct multiples of 16 rows
-        tally_sorted_kernel<<<grid, kTallyThreads, smem, st>>>(d_image_idx, d_class_idx, d_active, rows,
-                                                               int32_t(image_base), n_images, k, tile_images,
-                                                               d_counts, partials);
-        B2_LAUNCH_CHECK("tally_sorted_kernel");
+        if (tally_path_override() == 1) {                    // shared-memory tile kernel (comparison only)
+            B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_sorted_kernel), smem));
+            uint64_t want = (rows + 4ull * kBlockRows - 1) / (4ull * kBlockRows);
+            const uint64_t by_images = (uint64_t(n_images) + tile_images - 1) / tile_images;
+            if (want < by_images) want = by_images;
+            const uint64_t cap = 2ull * uint64_t(sm_count());
+            const uint32_t grid = uint32_t(want < 1 ? 1 : (want > cap ? cap : want));
+            tally_sorted_kernel<<<grid, kTallyThreads, smem, st>>>(d_image_idx, d_class_idx, d_active, rows,
+                                                                   int32_t(image_base), n_images, k, tile_images,
+                                                                   d_counts, partials);
+            B2_LAUNCH_CHECK("tally_sorted_kernel");
+            return B2_OK;
+        }
+        // one warp per ~4096 rows (or per 64 images when there are few rows), at most 6 CTAs of 8 warps per SM
+        const uint64_t warps_per_cta = kWarpKernelThreads / 32;
+        uint64_t want_warps = (rows + 4095) / 4096;
+        const uint64_t by_images = (uint64_t(n_images) + 63) / 64;
+        if (rows == 0 && want_warps < by_images) want_warps = by_images;
+        if (want_warps < 1) want_warps = 1;
+        const uint64_t cap = 6ull * uint64_t(sm_count()) * warps_per_cta;
+        if (want_warps > cap) want_warps = cap;
+        if (rows > 0 && want_warps > rows / kGroupRows) want_warps = rows / kGroupRows ? rows / kGroupRows : 1;
+        const uint64_t nw = want_warps;                       // distinct, 128-row aligned nominal starts
+        const uint32_t grid = uint32_t((nw + warps_per_cta - 1) / warps_per_cta);
+        const int32_t ib = int32_t(image_base);
+        if (k <= 32)
+            tally_warp_kernel<1><<<grid, kWarpKernelThreads, 0, st>>>(d_image_idx, d_class_idx, d_active, rows, ib, n_images, k, nw, d_counts, partials);
+        else if (k <= 64)
+            tally_warp_kernel<2><<<grid, kWarpKernelThreads, 0, st>>>(d_image_idx, d_class_idx, d_active, rows, ib, n_images, k, nw, d_counts, partials);
+        else if (k <= 128)
+            tally_warp_kernel<4><<<grid, kWarpKernelThreads, 0, st>>>(d_image_idx, d_class_idx, d_active, rows, ib, n_images, k, nw, d_counts, partials);
+        else
+            tally_warp_kernel<8><<<grid, kWarpKernelThreads, 0, st>>>(d_image_idx, d_class_idx, d_active, rows, ib, n_images, k, nw, d_counts, partials);
+        B2_LAUNCH_CHECK("tally_warp_kernel");
         return B2_OK;
     }
     B2_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, size_t(n_images) * k * 4, st));
