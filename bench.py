@@ -7,9 +7,9 @@ One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one
 synthetic input:
 
   ingest step  (headline `value`, images/s): `images_per_gpu` synthetic 1920x1080x3 images
-      (BASELINE config 2 shape) resident in HBM -> SHA-256 of every image, dedupe decision over
-      the digests, 256x256 uint8 thumbnail + float32 CHW preview of every image.  Hash
-      (INT32-ALU bound) and resize (HBM bound) run concurrently on two streams.
+      (BASELINE config 2 shape) resident in HBM -> 256x256 uint8 thumbnail + float32 CHW preview
+      of every image (HBM bound), SHA-256 of every image (INT32-ALU bound), dedupe decision over
+      the digests (+ digest all-gather at N > 1).
   label step   (`labels.value`, rows/s): BASELINE config 4 shape per GPU — 100 M rows, 1 M images,
       k = 50, clustered by image -> count matrix + integer Fleiss partials (+ all-reduce at N > 1).
 
@@ -155,7 +155,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_img = max(cores * 2, 32)
+    n_img = 64 * cores                                        # bounded sample: ~1.5 s per step on every core
     for _ in range(args.warmup):
         cpu_ingest_sample(min(n_img, cores), cores)
     tot_img = tot_t = 0.0
@@ -251,17 +251,21 @@ def run_graft(args):
 
     def ingest_step():
         main = torch.cuda.current_stream()
-        fork = torch.cuda.Event()
-        fork.record(main)
-        side.wait_event(fork)
-        with torch.cuda.stream(side):
+        if args.overlap:                                     # resize on a second stream, concurrently with the hash
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                plan.run(flat, offsets, thumb=thumbs, preview=previews)
+        else:
             plan.run(flat, offsets, thumb=thumbs, preview=previews)
         engine.sha256_device(flat, offsets, lengths, None, digests)
         if world > 1:
             is_new, counts = b2dist.global_dedupe(digests, global_index)
         else:
             is_new, _, _, counts = engine.dedupe_device(digests)
-        main.wait_stream(side)
+        if args.overlap:
+            main.wait_stream(side)
         launches["n"] += 4
         return is_new, counts
 
@@ -326,10 +330,13 @@ def run_graft(args):
 
     # ---------------- end to end: pinned host buffers through the pipeline ----------------
     e2e_n = min(args.e2e_images, n_img)
-    pipe = IngestPipeline(IMG_H, IMG_W, e2e_n, chunk_images=args.e2e_chunk, device=local_rank)
     host_images = torch.empty((e2e_n, IMG_BYTES), dtype=torch.uint8, pin_memory=True)
     host_images.copy_(data[:e2e_n])
     torch.cuda.synchronize()
+    ref_digests, ref_thumbs = digests[:e2e_n].clone(), thumbs[:8].clone()
+    del data, flat, thumbs, previews                          # make room: the pipeline stages the batch on device
+    torch.cuda.empty_cache()
+    pipe = IngestPipeline(IMG_H, IMG_W, e2e_n, chunk_images=args.e2e_chunk, device=local_rank)
     res = {}
 
     def e2e_step():
@@ -338,11 +345,10 @@ def run_graft(args):
     ms_e2e, _, _ = timed(e2e_step, max(2, args.steps // 2), 1)
     e2e_steps = max(2, args.steps // 2)
     e2e_value = e2e_n * world * e2e_steps / (ms_e2e / 1e3)
-    e2e_ok = bool(torch.equal(res["r"].digests.to(dev), digests[:e2e_n])) and \
-        bool(torch.equal(res["r"].thumbs[:8].to(dev), thumbs[:8]))
+    e2e_ok = bool(torch.equal(res["r"].digests.to(dev), ref_digests)) and \
+        bool(torch.equal(res["r"].thumbs[:8].to(dev), ref_thumbs))
     h2d, d2h = res["r"].h2d_bytes, res["r"].d2h_bytes
     del pipe, host_images
-    del data, flat, thumbs, previews
     torch.cuda.empty_cache()
 
     # ---------------- labels ----------------
@@ -406,7 +412,7 @@ def run_graft(args):
             return d
 
         cores = os.cpu_count() or 1
-        cpu_n = max(32, min(cores * 2, 256))
+        cpu_n = 512 * cores                                    # ~10-15 s of work on every core
         cpu_v, cpu_dt = cpu_ingest_sample(cpu_n, cores)
         line = {
             "metric": "ingest images/s", "value": value, "unit": "images/s", "n_gpus": world,
@@ -448,8 +454,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["graft", "reference"], default="graft")
     ap.add_argument("--images-per-gpu", type=int, default=0, help="default: 18944 (one hash warp per SM sub-partition)")
-    ap.add_argument("--e2e-images", type=int, default=2048)
-    ap.add_argument("--e2e-chunk", type=int, default=1024)
+    ap.add_argument("--e2e-images", type=int, default=4096)
+    ap.add_argument("--e2e-chunk", type=int, default=256)
+    ap.add_argument("--overlap", action="store_true", help="run resize on a second stream concurrently with the hash")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

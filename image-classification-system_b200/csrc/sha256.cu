@@ -51,11 +51,11 @@ struct Sha256State {
     }
 };
 
-// Integer add on the FMA pipe.  ncu on the first version of this kernel (profiles/r1_*): the ALU
-// pipe (SHF/LOP3/IADD3/PRMT, 16 lanes/clk per sub-partition) was 87 % busy and the FMA pipe 4 %.
-// Every rotate and boolean has to stay on the ALU pipe, but an add does not: `mad.lo x, 1, y`
-// is emitted as IMAD.IADD, which issues on the FMA pipe.  V = 0 leaves the choice to ptxas
-// (IADD3 on the ALU pipe), V >= 1 moves all 592 adds of a block.
+// Integer add, optionally forced onto the FMA pipe.  ncu on this kernel (profiles/r1_*): the ALU
+// pipe (SHF/LOP3/IADD3/PRMT) is 87 % busy and the FMA pipe 4 %.  Every rotate and boolean has to
+// stay on the ALU pipe, an add does not.  V = 0 leaves the choice to ptxas (mostly IADD3), V = 1
+// turns every add into an IMAD — an experiment that LOST (see sha_variant_override) and is kept
+// selectable for batches with several warps per sub-partition.
 template <int V>
 __device__ __forceinline__ uint32_t addp(uint32_t a, uint32_t b, uint32_t one) {
     if (V == 0) return a + b;
@@ -331,10 +331,13 @@ static int sha_path_override() {
     return e ? atoi(e) : 0;
 }
 
-// B2_SHA_VARIANT: 0 = adds left to ptxas (ALU pipe), 1 = adds forced onto the FMA pipe (default).
+// B2_SHA_VARIANT: 0 = adds left to ptxas (default), 1 = adds forced onto the FMA pipe.  Measured on
+// B200 with one warp per SM sub-partition (all that 1080p images leave room for in HBM): variant 0
+// 825 GB/s, variant 1 560 GB/s — a lone warp issues one instruction every ~2 cycles whatever the
+// pipe, so what counts is the instruction count (IADD3 adds three operands, IMAD two).
 static int sha_variant_override() {
     const char *e = getenv("B2_SHA_VARIANT");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
 }
 
 extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,

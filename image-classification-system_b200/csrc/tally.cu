@@ -295,40 +295,54 @@ tally_sorted_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__rest
 }
 
 // ----------------------------------------------------------------------------------------
-// tally_warp_kernel<NG> — the product kernel for rows ordered by image_idx.  No shared-memory
-// atomics at all (measured: ~2 cycles per lane, the bottleneck of the tile kernel above):
+// tally_warp_kernel — the product kernel for rows ordered by image_idx.  No atomics on the row
+// path at all (measured: shared-memory atomics cost ~2 cycles per lane and bound the tile
+// kernel above at 22 % of HBM peak):
 //   * A WARP streams a contiguous row range and owns the images that START in it (same
 //     ownership rule as above, per warp instead of per CTA).
-//   * Lane l owns the counters of classes {l, l+32, ...} of the image being accumulated, in
-//     REGISTERS (NG = ceil(k/32) of them).  A group of 128 rows is loaded as four steps of 32
-//     consecutive rows (coalesced 128-byte / 32-byte requests), the next group is prefetched
-//     into registers.  Per step the class values are bit-sliced with warp ballots (one
-//     ballot per class bit); lane l ANDs the slices that spell its class numbers, masks with
-//     the ballot of "active, in range, same image" and adds the population count.
-//   * When the image changes, each lane stores its counters straight to d_counts — one
-//     coalesced k*4-byte store per image, no tile, no flush — and folds them into its own
-//     class totals / sum of squares.  n_i is the population count of the row mask, uniform
-//     across the warp, so R, rated images and pairs need no reduction at all.
+//   * Rows reach the warp through its own ring of two shared-memory stages of 256 rows filled by
+//     the bulk-copy (TMA) engine (cp.async.bulk + mbarrier, three 1-D copies per stage issued by
+//     one lane): the next stage is in flight while this one is tallied, without holding registers.
+//   * A step is 32 consecutive rows, one per lane.  MATCH.ANY on the class byte gives every lane
+//     the set of lanes with its class; ANDed with the ballot of "active, in range, current
+//     image" it is the group whose size is the increment.  The lowest lane of each group adds
+//     it to the warp's PRIVATE k-entry counter array in shared memory with a plain
+//     read-modify-write: groups have distinct classes, so there are no conflicts and no atomics.
+//   * When the image changes the lanes copy the k counters to d_counts — one coalesced k*4-byte
+//     store per image, no tile, no flush — zero them and fold them into per-warp class totals
+//     and the sum of squares.  n_i is the population count of the row mask, uniform across the
+//     warp, so R, rated images and pairs need no reduction.
 //   * Partials are combined per CTA in shared memory, then one 64-bit atomic per value and CTA.
 // ----------------------------------------------------------------------------------------
 constexpr int kWarpKernelThreads = 256;
-constexpr int kGroupRows = 128;
+constexpr int kWarpsPerCta = kWarpKernelThreads / 32;
+constexpr int kStageRows = 256;
+constexpr int kGroupRows = kStageRows;                        // nominal starts are aligned to one stage
+constexpr int kStageBytes = kStageRows * 6;                   // int32 image + uint8 class + uint8 active
+constexpr int kStages = 2;
+constexpr int kWarpSmemBytes = kStages * kStageBytes + 256 * 4 + 256 * 8;            // ring + counters + class totals
+constexpr int kWarpKernelSmem = kWarpsPerCta * kWarpSmemBytes;                       // 48 KB per CTA, four CTAs per SM
 
-template <int NG>
-__global__ void __launch_bounds__(kWarpKernelThreads)
+__global__ void __launch_bounds__(kWarpKernelThreads, 4)
 tally_warp_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
                   const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
                   uint32_t k, uint64_t n_workers, int32_t *__restrict__ counts,
                   unsigned long long *__restrict__ g_partials) {
-    constexpr int NBITS = NG == 1 ? 5 : (NG == 2 ? 6 : (NG == 4 ? 7 : 8));
     __shared__ unsigned long long s_tot[256 + 8];
+    extern __shared__ __align__(128) uint8_t warp_smem[];
+    __shared__ __align__(8) uint64_t ring_bars[kWarpsPerCta * kStages];
     for (uint32_t i = threadIdx.x; i < 256 + 8; i += blockDim.x) s_tot[i] = 0;
+
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t *my = warp_smem + size_t(wid) * kWarpSmemBytes;
+    uint32_t *cnt_s = reinterpret_cast<uint32_t *>(my + kStages * kStageBytes);             // k counters of image `cur`
+    unsigned long long *tot_s = reinterpret_cast<unsigned long long *>(my + kStages * kStageBytes + 256 * 4);
+    for (uint32_t c = lane; c < 256; c += 32) { cnt_s[c] = 0; tot_s[c] = 0; }
     __syncthreads();
 
-    const uint32_t lane = threadIdx.x & 31;
-    // n_workers warps share the rows; the host keeps it <= rows/128 so that nominal starts are distinct
+    // n_workers warps share the rows; the host keeps it <= rows/512 so that nominal starts are distinct
     const uint64_t W = n_workers;
-    const uint64_t w = uint64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t w = uint64_t(blockIdx.x) * kWarpsPerCta + wid;
     const bool worker = w < W;
     const int32_t img_end_all = image_base + int32_t(n_images);
     auto nominal = [&](uint64_t i) -> uint64_t {
@@ -350,31 +364,26 @@ tally_warp_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
         I1 = w + 1 == W ? img_end_all : boundary(nom1);
         if (I1 < I0) I1 = I0;                                 // unsorted input
     }
+    const int32_t span = I1 - I0;                             // "mine" <=> unsigned(img - I0) < span
+    const uint32_t lanes_below = (1u << lane) - 1u;
 
-    // inv[b]: all-ones when bit b of this lane's class numbers is 0 (so slice ^ inv selects "bit == mine")
-    uint32_t inv[5];
-#pragma unroll
-    for (int b = 0; b < 5; ++b) inv[b] = ((lane >> b) & 1u) ? 0u : 0xffffffffu;
-
-    uint32_t cnt[NG];
-    unsigned long long tot[NG];
-#pragma unroll
-    for (int g = 0; g < NG; ++g) { cnt[g] = 0; tot[g] = 0; }
     unsigned long long s2 = 0, sum_r = 0, pairs = 0;
     uint32_t rated = 0, pair_images = 0, seen = 0, unsorted = 0, n_cur = 0;
     int32_t cur = I0;
 
     // store the finished image, fold it into the partials, zero-fill images without rows up to `next`
     auto finish_image = [&](int32_t next) {
+        __syncwarp();
         if (cur < I1) {
             int32_t *dst = counts + size_t(cur - image_base) * k;
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const uint32_t c = lane + 32u * g;
-                if (c < k) dst[c] = int32_t(cnt[g]);
-                tot[g] += cnt[g];
-                s2 += (unsigned long long)cnt[g] * cnt[g];
-                cnt[g] = 0;
+            for (uint32_t c = lane; c < k; c += 32) {
+                const uint32_t v = cnt_s[c];
+                dst[c] = int32_t(v);
+                if (v) {
+                    cnt_s[c] = 0;
+                    tot_s[c] += v;
+                    s2 += (unsigned long long)v * v;
+                }
             }
             sum_r += n_cur;
             rated += n_cur >= 1;
@@ -384,102 +393,117 @@ tally_warp_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
             const int32_t stop = next < I1 ? next : I1;
             for (int32_t img = cur + 1; img < stop; ++img) {
                 int32_t *z = counts + size_t(img - image_base) * k;
-#pragma unroll
-                for (int g = 0; g < NG; ++g)
-                    if (lane + 32u * g < k) z[lane + 32u * g] = 0;
+                for (uint32_t c = lane; c < k; c += 32) z[c] = 0;
             }
         }
         cur = next;
+        __syncwarp();
     };
 
-    // A group is 128 consecutive rows; in step s lane l holds row grp + 32*s + l, so the rows of a
-    // step are consecutive and (for ordered input) images never go backwards from step to step.
-    struct Group { int32_t idx[4]; uint32_t cls[4], act[4]; };
-    auto load_group = [&](uint64_t grp) -> Group {
-        Group q;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const uint64_t r = grp + 32ull * s + lane;
-            q.idx[s] = INT32_MAX;                            // past the table: sorts last, owned by nobody
-            q.cls[s] = 0;
-            q.act[s] = 0;
-            if (r < rows) {
-                q.idx[s] = __ldg(image_idx + r);
-                q.cls[s] = __ldg(class_idx + r);
-                q.act[s] = __ldg(active + r);
-            }
+    // add the rows of `vm` (a ballot: rows of image `cur` that count) to the warp's counters
+    auto accumulate = [&](uint32_t same_class, uint32_t vm, uint32_t c) {
+        const uint32_t grp = same_class & vm;                 // rows with my class that count
+        if (((vm >> lane) & 1u) && (grp & lanes_below) == 0) cnt_s[c] += __popc(grp);   // lowest lane of the group
+        n_cur += __popc(vm);
+    };
+
+    // one step of 32 consecutive rows; returns false once the stream has left this warp's images
+    auto step = [&](int32_t img, uint32_t c, uint32_t act, int32_t prev_img, bool check_order) -> bool {
+        if (check_order) {
+            // lane l > 0 compares with lane l-1 of this step, lane 0 with lane 31 of the previous one
+            const int32_t z = lane == 31 ? prev_img : img;
+            const int32_t before = __shfl_sync(0xffffffffu, z, (lane + 31) & 31);
+            unsorted += (img < before) & (img != INT32_MAX);
         }
-        return q;
+        if (span <= 0) return false;                          // this warp owns no image: order check only
+        const uint32_t same_class = __match_any_sync(0xffffffffu, c);
+        const bool good = (c < k) & (act != 0);
+        if (__all_sync(0xffffffffu, img == cur)) {            // common case: one image, the current one
+            seen += c < k;
+            accumulate(same_class, __ballot_sync(0xffffffffu, good), c);
+            __syncwarp();
+            return true;
+        }
+        const bool mine = uint32_t(img - I0) < uint32_t(span);
+        seen += mine & (c < k);
+        uint32_t rem = __ballot_sync(0xffffffffu, mine);
+        while (rem) {
+            const int first = __ffs(rem) - 1;
+            const int32_t nxt = __shfl_sync(0xffffffffu, img, first);
+            if (nxt != cur) finish_image(nxt);
+            const uint32_t same = __ballot_sync(0xffffffffu, img == nxt) & rem;
+            accumulate(same_class, __ballot_sync(0xffffffffu, mine & good & (img == nxt)), c);
+            __syncwarp();
+            rem &= ~same;
+        }
+        return __any_sync(0xffffffffu, img < I1) != 0;
     };
 
-    if (worker && nom0 < rows) {
-        int32_t carry = nom0 > 0 ? __ldg(image_idx + nom0 - 1) : INT32_MIN;   // last row before the step (order check)
-        Group q = load_group(nom0);
-        for (uint64_t grp = nom0; grp < rows; grp += kGroupRows) {
-            Group nq;
-            const bool has_next = grp + kGroupRows < rows;
-            if (has_next) nq = load_group(grp + kGroupRows);
-
+    if (worker && nom0 < rows && span >= 0) {
+        int32_t *s_idx = reinterpret_cast<int32_t *>(my);
+        uint64_t *bars = ring_bars + wid * kStages;
+        auto stage_idx = [&](int b) { return s_idx + b * (kStageBytes / 4); };
+        auto stage_cls = [&](int b) { return reinterpret_cast<uint8_t *>(stage_idx(b)) + kStageRows * 4; };
+        auto stage_act = [&](int b) { return stage_cls(b) + kStageRows; };
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < kStages; ++b) mbar_init(&bars[b], 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        const uint64_t n_stage = (rows - nom0 + kStageRows - 1) / kStageRows;    // upper bound; the stream usually ends earlier
+        auto issue = [&](uint64_t st) {                       // whole warp calls; lane 0 issues
+            const uint64_t r0 = nom0 + st * kStageRows;
+            const int b = int(st % kStages);
+            if (r0 + kStageRows <= rows) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&bars[b], kStageRows * 6);
+                    bulk_g2s(stage_idx(b), image_idx + r0, kStageRows * 4, &bars[b]);
+                    bulk_g2s(stage_cls(b), class_idx + r0, kStageRows, &bars[b]);
+                    bulk_g2s(stage_act(b), active + r0, kStageRows, &bars[b]);
+                }
+            } else {                                          // ragged end of the table: plain loads, sentinel fill
+                for (int i = lane; i < kStageRows; i += 32) {
+                    const bool in = r0 + i < rows;
+                    stage_idx(b)[i] = in ? image_idx[r0 + i] : INT32_MAX;        // sorts last, owned by nobody
+                    stage_cls(b)[i] = in ? class_idx[r0 + i] : uint8_t(0);
+                    stage_act(b)[i] = in ? active[r0 + i] : uint8_t(0);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[b]);
+            }
+        };
+        int32_t prev_img = nom0 > 0 ? __ldg(image_idx + nom0 - 1) : INT32_MIN;   // row before the first
+        const bool owns = span > 0;
+        uint64_t issued = 0, st = 0;
+        for (; issued < kStages - 1 && issued < n_stage; ++issued) issue(issued);
+        for (; st < n_stage; ++st) {
+            if (issued < n_stage) { issue(issued); ++issued; }
+            const int b = int(st % kStages);
+            mbar_wait(&bars[b], uint32_t((st / kStages) & 1));
+            const int32_t *si = stage_idx(b) + lane;
+            const uint8_t *sc = stage_cls(b) + lane, *sa = stage_act(b) + lane;
+            const uint64_t r0 = nom0 + st * kStageRows;
+            const bool check_order = r0 < nom1;               // nom1 is stage aligned (or the table end)
             bool any_mine = false;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const int32_t img = q.idx[s];
-                const uint32_t c = q.cls[s];
-                const bool a = q.act[s] != 0;
-                // order check of the pairs (r-1, r), nom0 <= r < nom1, this warp is responsible for
-                {
-                    int32_t before = __shfl_up_sync(0xffffffffu, img, 1);
-                    if (lane == 0) before = carry;
-                    unsorted += (img < before) & (grp < nom1) & (img != INT32_MAX);
-                    carry = __shfl_sync(0xffffffffu, img, 31);
-                }
-                const bool mine = (img >= I0) & (img < I1);
-                const bool ok = mine & (c < k);
-                seen += ok;
-                any_mine |= img < I1;
-                uint32_t slice[NBITS];
-#pragma unroll
-                for (int b = 0; b < NBITS; ++b) slice[b] = __ballot_sync(0xffffffffu, (c >> b) & 1u);
-                uint32_t low = slice[0] ^ inv[0];
-#pragma unroll
-                for (int b = 1; b < 5; ++b) low &= slice[b] ^ inv[b];
-
-                auto accumulate = [&](uint32_t vm) {          // vm: rows of image `cur` that count
-#pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        uint32_t m = low & vm;
-#pragma unroll
-                        for (int b = 5; b < NBITS; ++b) m &= ((g >> (b - 5)) & 1) ? slice[b] : ~slice[b];
-                        cnt[g] += __popc(m);
-                    }
-                    n_cur += __popc(vm);
-                };
-
-                if (__all_sync(0xffffffffu, mine & (img == cur))) {       // common case: one image, all mine
-                    accumulate(__ballot_sync(0xffffffffu, ok & a));
-                } else {
-                    uint32_t rem = __ballot_sync(0xffffffffu, mine);
-                    while (rem) {
-                        const int first = __ffs(rem) - 1;
-                        const int32_t nxt = __shfl_sync(0xffffffffu, img, first);
-                        if (nxt != cur) finish_image(nxt);
-                        const uint32_t same = __ballot_sync(0xffffffffu, img == nxt) & rem;
-                        accumulate(__ballot_sync(0xffffffffu, ok & a & (img == nxt)));
-                        rem &= ~same;
-                    }
-                }
+#pragma unroll 4
+            for (int t = 0; t < kStageRows / 32; ++t) {
+                const int32_t img = si[32 * t];
+                any_mine |= step(img, sc[32 * t], sa[32 * t], prev_img, check_order);
+                prev_img = img;
             }
-            // past the nominal end and nothing of this group is below I1: the stream has left my images
-            if (grp + kGroupRows >= nom1 && !__any_sync(0xffffffffu, any_mine)) break;
-            q = nq;
+            __syncwarp();                                     // every lane is done with this stage before it is refilled
+            // past the nominal end with nothing below I1 in this stage: the stream has left my images
+            if (r0 + kStageRows >= nom1 && !(any_mine && owns)) { ++st; break; }
         }
+        // stages issued but not consumed: their copies must land before this CTA's shared memory is released
+        for (; st < issued; ++st) mbar_wait(&bars[st % kStages], uint32_t((st / kStages) & 1));
     }
     finish_image(I1);
 
     // ---- commit: warp -> CTA (shared, 64-bit) -> global (one atomic per value and CTA) ----
-#pragma unroll
-    for (int g = 0; g < NG; ++g)
-        if (tot[g]) atomicAdd(&s_tot[lane + 32 * g], tot[g]);
+    for (uint32_t c = lane; c < k; c += 32)
+        if (tot_s[c]) atomicAdd(&s_tot[c], tot_s[c]);
     {
         const unsigned long long v_s2 = warp_sum(s2), v_seen = warp_sum(seen), v_uns = warp_sum(unsorted);
         if (lane == 0) {
@@ -645,26 +669,21 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
             B2_LAUNCH_CHECK("tally_sorted_kernel");
             return B2_OK;
         }
-        // one warp per ~4096 rows (or per 64 images when there are few rows), at most 6 CTAs of 8 warps per SM
+        // one warp per ~4096 rows (or per 64 images when there are no rows), at most one resident wave
         const uint64_t warps_per_cta = kWarpKernelThreads / 32;
         uint64_t want_warps = (rows + 4095) / 4096;
         const uint64_t by_images = (uint64_t(n_images) + 63) / 64;
         if (rows == 0 && want_warps < by_images) want_warps = by_images;
         if (want_warps < 1) want_warps = 1;
-        const uint64_t cap = 6ull * uint64_t(sm_count()) * warps_per_cta;
+        const uint64_t cap = 4ull * uint64_t(sm_count()) * warps_per_cta;   // 4 CTAs of 8 warps per SM (48 KB each): one wave
         if (want_warps > cap) want_warps = cap;
         if (rows > 0 && want_warps > rows / kGroupRows) want_warps = rows / kGroupRows ? rows / kGroupRows : 1;
         const uint64_t nw = want_warps;                       // distinct, 128-row aligned nominal starts
         const uint32_t grid = uint32_t((nw + warps_per_cta - 1) / warps_per_cta);
-        const int32_t ib = int32_t(image_base);
-        if (k <= 32)
-            tally_warp_kernel<1><<<grid, kWarpKernelThreads, 0, st>>>(d_image_idx, d_class_idx, d_active, rows, ib, n_images, k, nw, d_counts, partials);
-        else if (k <= 64)
-            tally_warp_kernel<2><<<grid, kWarpKernelThreads, 0, st>>>(d_image_idx, d_class_idx, d_active, rows, ib, n_images, k, nw, d_counts, partials);
-        else if (k <= 128)
-            tally_warp_kernel<4><<<grid, kWarpKernelThreads, 0, st>>>(d_image_idx, d_class_idx, d_active, rows, ib, n_images, k, nw, d_counts, partials);
-        else
-            tally_warp_kernel<8><<<grid, kWarpKernelThreads, 0, st>>>(d_image_idx, d_class_idx, d_active, rows, ib, n_images, k, nw, d_counts, partials);
+        B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_warp_kernel), kWarpKernelSmem));
+        tally_warp_kernel<<<grid, kWarpKernelThreads, kWarpKernelSmem, st>>>(d_image_idx, d_class_idx, d_active, rows,
+                                                                            int32_t(image_base), n_images, k, nw,
+                                                                            d_counts, partials);
         B2_LAUNCH_CHECK("tally_warp_kernel");
         return B2_OK;
     }

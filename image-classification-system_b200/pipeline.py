@@ -3,10 +3,12 @@
     pinned host images --H2D--> [sha256 | resize+normalise] --D2H--> digests, thumbnails, previews
                                          \\--> dedupe over the whole batch --D2H--> flags + stats
 
-Chunks are double-buffered over two CUDA streams so the copy of chunk c+1 overlaps the kernels of
-chunk c; hashing (INT32-ALU bound) and resizing (HBM bound) of one chunk run concurrently on two
-further streams.  The chunk must be large enough to give the hash kernel its parallelism (one lane
-per image): ~1000 images of 1080p keep PCIe, not the hash latency, the limit.
+SHA-256 is serial per message: one lane hashes one image at ~48 MB/s, so a 1080p image takes
+~130 ms however few images are in flight.  The pipeline therefore copies the batch in small chunks
+on ONE copy stream and launches each chunk's hash kernel on one of several compute streams, so many
+hash kernels (8 warps each) overlap each other and the remaining copies; PCIe, not the hash latency,
+is the limit for batches of a few thousand images.  Resize (HBM bound, ~3 us per image) follows each
+chunk on a second set of streams and its outputs are copied back while later chunks still arrive.
 """
 from __future__ import annotations
 
@@ -30,30 +32,30 @@ class PipelineResult:
 
 
 class IngestPipeline:
-    def __init__(self, in_h: int, in_w: int, max_images: int, chunk_images: int = 1024, out_h: int = 256,
-                 out_w: int = 256, want_preview: bool = True, device: Optional[int] = None):
+    def __init__(self, in_h: int, in_w: int, max_images: int, chunk_images: int = 256, out_h: int = 256,
+                 out_w: int = 256, want_preview: bool = True, device: Optional[int] = None, n_streams: int = 8):
         self.dev = torch.device("cuda", engine.init(device))
         self.in_h, self.in_w, self.out_h, self.out_w = in_h, in_w, out_h, out_w
         self.L = in_h * in_w * 3
-        assert self.L % 16 == 0, "fixed-shape pipeline needs 16-byte aligned image size"
-        self.chunk = min(chunk_images, max_images)
+        assert self.L % 16 == 0, "fixed-shape pipeline needs a 16-byte aligned image size"
+        self.chunk = max(1, min(chunk_images, max_images))
         self.max_images = max_images
         self.plan = engine.get_plan(in_h, in_w, out_h, out_w, self.dev.index)
         dev = self.dev
-        self.stage = [torch.empty(self.chunk * self.L, dtype=torch.uint8, device=dev) for _ in range(2)]
-        self.offsets = torch.arange(self.chunk, dtype=torch.int64, device=dev) * self.L
-        self.lengths = torch.full((self.chunk,), self.L, dtype=torch.int64, device=dev)
+        self.stage = torch.empty(max_images * self.L, dtype=torch.uint8, device=dev)      # whole batch resident
+        self.offsets = torch.arange(max_images, dtype=torch.int64, device=dev) * self.L
+        self.lengths = torch.full((max_images,), self.L, dtype=torch.int64, device=dev)
         self.d_digests = torch.empty((max_images, 32), dtype=torch.uint8, device=dev)
-        self.d_thumbs = [torch.empty((self.chunk, out_h, out_w, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
-        self.d_prev = [torch.empty((self.chunk, 3, out_h, out_w), dtype=torch.float32, device=dev)
-                       for _ in range(2)] if want_preview else None
+        self.d_thumbs = torch.empty((max_images, out_h, out_w, 3), dtype=torch.uint8, device=dev)
+        self.d_prev = torch.empty((max_images, 3, out_h, out_w), dtype=torch.float32, device=dev) if want_preview else None
         pin = dict(pin_memory=True)
         self.h_digests = torch.empty((max_images, 32), dtype=torch.uint8, **pin)
         self.h_is_new = torch.empty(max_images, dtype=torch.uint8, **pin)
         self.h_counts = torch.empty(3, dtype=torch.int32, **pin)
         self.h_thumbs = torch.empty((max_images, out_h, out_w, 3), dtype=torch.uint8, **pin)
         self.h_prev = torch.empty((max_images, 3, out_h, out_w), dtype=torch.float32, **pin) if want_preview else None
-        self.copy_streams = [torch.cuda.Stream(dev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.hash_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
         self.resize_streams = [torch.cuda.Stream(dev) for _ in range(2)]
         self.kernel_launches = 0
 
@@ -64,38 +66,39 @@ class IngestPipeline:
         main = torch.cuda.current_stream(self.dev)
         start = torch.cuda.Event()
         start.record(main)
+        self.copy_stream.wait_event(start)
+        for s in self.hash_streams + self.resize_streams:
+            s.wait_event(start)
         h2d = d2h = 0
         self.kernel_launches = 0
         flat = host_images.view(n, self.L)
         for c, lo in enumerate(range(0, n, self.chunk)):
             hi = min(lo + self.chunk, n)
             m = hi - lo
-            b = c & 1
-            cs, rs = self.copy_streams[b], self.resize_streams[b]
-            cs.wait_event(start)
-            with torch.cuda.stream(cs):
-                stage = self.stage[b][: m * self.L]
-                stage.copy_(flat[lo:hi].reshape(-1), non_blocking=True)
+            dev_chunk = self.stage[lo * self.L: hi * self.L]
+            with torch.cuda.stream(self.copy_stream):
+                dev_chunk.copy_(flat[lo:hi].reshape(-1), non_blocking=True)
                 h2d += m * self.L
                 copied = torch.cuda.Event()
-                copied.record(cs)
-                engine.sha256_device(stage, self.offsets[:m], self.lengths[:m], None, self.d_digests[lo:hi])
+                copied.record(self.copy_stream)
+            hs = self.hash_streams[c % len(self.hash_streams)]
+            with torch.cuda.stream(hs):
+                hs.wait_event(copied)
+                engine.sha256_device(self.stage, self.offsets[lo:hi], self.lengths[lo:hi], None, self.d_digests[lo:hi])
                 self.kernel_launches += 1
+            rs = self.resize_streams[c % len(self.resize_streams)]
             with torch.cuda.stream(rs):
                 rs.wait_event(copied)
-                thumbs = self.d_thumbs[b][:m]
-                prev = self.d_prev[b][:m] if self.d_prev is not None else None
-                self.plan.run(stage, self.offsets[:m], thumb=thumbs, preview=prev, want_preview=prev is not None)
+                thumbs = self.d_thumbs[lo:hi]
+                prev = self.d_prev[lo:hi] if self.d_prev is not None else None
+                self.plan.run(self.stage, self.offsets[lo:hi], thumb=thumbs, preview=prev, want_preview=prev is not None)
                 self.kernel_launches += 1
                 self.h_thumbs[lo:hi].copy_(thumbs, non_blocking=True)
                 d2h += thumbs.numel()
                 if prev is not None:
                     self.h_prev[lo:hi].copy_(prev, non_blocking=True)
                     d2h += prev.numel() * 4
-                done = torch.cuda.Event()
-                done.record(rs)
-            cs.wait_event(done)                    # the staging buffer is reused two chunks later
-        for s in self.copy_streams + self.resize_streams:
+        for s in [self.copy_stream] + self.hash_streams + self.resize_streams:
             main.wait_stream(s)
         is_new, first, last, counts = engine.dedupe_device(self.d_digests[:n], existing_sorted=existing_sorted)
         self.kernel_launches += 2
