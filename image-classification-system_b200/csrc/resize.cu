@@ -88,16 +88,15 @@ struct b2_resize_plan {
     int device;
     int32_t *d_hbounds, *d_hcoeffs, *d_vbounds, *d_vcoeffs;
     // fast-path geometry
-    int band_rows;        // output rows per CTA
-    int n_bands;
-    int max_band_in_rows; // max input rows any band needs
+    int tmp_ring_rows;    // rows of the rolling intermediate (power of two)
     int rows_per_stage;
     int stage_bytes;      // bytes of one ring stage (incl. alignment + over-read padding)
     int n_stages;
     int tmp_pitch;        // bytes per intermediate row (multiple of 16)
     int threads;
     int ksh_bucket;       // template bucket for horizontal taps (0 = fast path unavailable)
-    size_t smem_bytes;
+    size_t smem_fixed;    // ring + intermediate (+ slack); the vertical tap tables add band_rows*(2+ksize_v)*4
+    size_t smem_max;      // with band_rows = out_h
 };
 
 namespace b2 {
@@ -114,7 +113,7 @@ struct ResizeParams {
     int in_h, in_w, out_h, out_w;
     int ksize_h, ksize_v;
     int band_rows, n_bands, max_band_in_rows;
-    int rows_per_stage, stage_bytes, n_stages, tmp_pitch;
+    int rows_per_stage, stage_bytes, n_stages, tmp_pitch, tmp_ring_rows;
     float mean[3], inv_std[3];
 };
 
@@ -129,7 +128,14 @@ __device__ __forceinline__ float normalise(uint32_t u8, float mean, float inv_st
     return __fmul_rn(__fsub_rn(__fmul_rn(float(u8), 1.0f / 255.0f), mean), inv_std);
 }
 
-template <int KSH>
+// BILINEAR taps are non-negative and sum to 2^22 +- ksize/2, so 2^21 + sum(px*k) >> 22 is already inside
+// 0..255 and the clip is dead code; kClip = true keeps it for filters with negative lobes.
+template <bool kClip>
+__device__ __forceinline__ uint32_t to_u8(int32_t acc) {
+    return kClip ? clip8(acc) : uint32_t(acc) >> kPrecisionBits;
+}
+
+template <int KSH, bool kClip = false>
 __global__ void __launch_bounds__(256)
 resize_bands_kernel(const ResizeParams p) {
     constexpr int NV = (3 * KSH + 3) / 4;       // byte-aligned window, in 32-bit words
@@ -151,9 +157,10 @@ resize_bands_kernel(const ResizeParams p) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(img_ptr)) & 15) == 0;
 
     uint8_t *ring = smem;                                            // n_stages * stage_bytes
-    uint8_t *tmp = smem + size_t(p.n_stages) * p.stage_bytes;        // max_band_in_rows * tmp_pitch
-    int32_t *vb_s = reinterpret_cast<int32_t *>(tmp + size_t(p.max_band_in_rows) * p.tmp_pitch);  // band_rows*2
+    uint8_t *tmp = smem + size_t(p.n_stages) * p.stage_bytes;        // tmp_ring_rows * tmp_pitch (rolling)
+    int32_t *vb_s = reinterpret_cast<int32_t *>(tmp + size_t(p.tmp_ring_rows) * p.tmp_pitch);     // band_rows*2
     int32_t *vk_s = vb_s + 2 * p.band_rows;                          // band_rows * ksize_v
+    const int tmp_mask = p.tmp_ring_rows - 1;                        // power of two
 
     if (tid == 0) {
         for (int s = 0; s < p.n_stages; ++s) mbar_init(&full_bar[s], 1);
@@ -189,14 +196,13 @@ resize_bands_kernel(const ResizeParams p) {
         b0 = uint64_t(ra) * pitch;
         b1 = uint64_t(rb) * pitch;
     };
-    auto issue = [&](int s) {          // thread 0 only, aligned images only
+    auto issue = [&](int s, int buf) { // thread 0 only, aligned images only
         uint64_t b0, b1;
         stage_range(s, b0, b1);
         const uint64_t a0 = b0 & ~uint64_t(15);
         uint64_t a1 = (b1 + 15) & ~uint64_t(15);
         const uint64_t lim = img_bytes & ~uint64_t(15);
         if (a1 > lim) a1 = lim;
-        const int buf = s % p.n_stages;
         const uint32_t bytes = a1 > a0 ? uint32_t(a1 - a0) : 0u;
         if (bytes) {
             mbar_arrive_expect_tx(&full_bar[buf], bytes);
@@ -207,18 +213,68 @@ resize_bands_kernel(const ResizeParams p) {
     };
 
     if (aligned && tid == 0) {
-        for (int s = 0; s < p.n_stages - 1 && s < total_stages; ++s) issue(s);
+        for (int s = 0; s < p.n_stages - 1 && s < total_stages; ++s) issue(s, s);
     }
 
+    // ---- vertical pass, run incrementally: after every stage the output rows whose taps are all in
+    // the rolling intermediate are finished and written.  The intermediate is a ring of tmp_ring_rows
+    // (>= 2*rows_per_stage + ksize_v + 2) rows, so a band can be the whole image: no input row is read
+    // or filtered twice, and the next stage's horizontal pass never overwrites a row still being read.
+    const int row_bytes = p.out_w * 3;
+    const uint32_t slot = p.out_slot ? p.out_slot[img] : uint32_t(img);
+    uint8_t *thumb = p.thumb + uint64_t(slot) * p.out_h * row_bytes;
+    float *prev = p.preview ? p.preview + uint64_t(slot) * 3 * p.out_h * p.out_w : nullptr;
+    int next_oy = oy0;                                               // uniform: first output row not yet written
+    // One thread per output PIXEL (thread x = column x, as in the horizontal pass): every warp gets the
+    // same share of a finished row, so nobody idles at the per-stage barrier, and the float32 CHW
+    // preview is written with fully coalesced 128-byte stores.
+    const float mean0 = p.mean[0], mean1 = p.mean[1], mean2 = p.mean[2];
+    const float istd0 = p.inv_std[0], istd1 = p.inv_std[1], istd2 = p.inv_std[2];
+    auto emit_ready = [&](int rows_done) {
+        int e1 = next_oy;
+        while (e1 < oy1 && vb_s[2 * (e1 - oy0)] + vb_s[2 * (e1 - oy0) + 1] <= rows_done) ++e1;
+        if (col_active) {
+            for (int oy = next_oy; oy < e1; ++oy) {
+                const int ly = oy - oy0;
+                const int ymin = vb_s[2 * ly], cnt = vb_s[2 * ly + 1];
+                const int32_t *vk = vk_s + ly * p.ksize_v;
+                int32_t a0 = kRound, a1 = kRound, a2 = kRound;
+                const uint8_t *col = tmp + 3 * tid;
+                int rr = ymin - r0;
+                for (int t = 0; t < cnt; ++t, ++rr) {
+                    const uint8_t *px = col + size_t(rr & tmp_mask) * p.tmp_pitch;
+                    const int32_t k = vk[t];
+                    a0 += int32_t(px[0]) * k;
+                    a1 += int32_t(px[1]) * k;
+                    a2 += int32_t(px[2]) * k;
+                }
+                const uint32_t o0 = to_u8<kClip>(a0), o1 = to_u8<kClip>(a1), o2 = to_u8<kClip>(a2);
+                uint8_t *tpx = thumb + size_t(oy) * row_bytes + 3 * tid;
+                tpx[0] = uint8_t(o0); tpx[1] = uint8_t(o1); tpx[2] = uint8_t(o2);
+                if (prev) {
+                    float *pp = prev + size_t(oy) * p.out_w + tid;
+                    const size_t plane = size_t(p.out_h) * p.out_w;
+                    pp[0] = normalise(o0, mean0, istd0);
+                    pp[plane] = normalise(o1, mean1, istd1);
+                    pp[2 * plane] = normalise(o2, mean2, istd2);
+                }
+            }
+        }
+        next_oy = e1;
+    };
+
+    // ring position of stage s (buf), of the stage issued this iteration (ibuf) and the parity of buf's
+    // barrier are carried along instead of being recomputed with % and / every stage
+    int buf = 0, ibuf = p.n_stages - 1;
+    uint32_t parity = 0;
     for (int s = 0; s < total_stages; ++s) {
-        const int buf = s % p.n_stages;
         uint8_t *sbuf = ring + size_t(buf) * p.stage_bytes;
         uint64_t b0, b1;
         stage_range(s, b0, b1);
         const uint64_t a0 = b0 & ~uint64_t(15);
         if (aligned) {
-            if (tid == 0 && s + p.n_stages - 1 < total_stages) issue(s + p.n_stages - 1);
-            mbar_wait(&full_bar[buf], uint32_t((s / p.n_stages) & 1));
+            if (tid == 0 && s + p.n_stages - 1 < total_stages) issue(s + p.n_stages - 1, ibuf);
+            mbar_wait(&full_bar[buf], parity);
             const uint64_t lim = img_bytes & ~uint64_t(15);
             if (b1 > lim) {            // ragged image tail: uniform branch, last stage of last band
                 for (uint64_t b = max(lim, a0) + tid; b < b1; b += blockDim.x) sbuf[b - a0] = img_ptr[b];
@@ -232,9 +288,9 @@ resize_bands_kernel(const ResizeParams p) {
         const int ra = r0 + s * p.rows_per_stage;
         const int rb = min(ra + p.rows_per_stage, r1);
         if (col_active) {
-            for (int r = ra; r < rb; ++r) {
-                // byte address (in shared memory) of my first source byte
-                const uint32_t src = smem_u32(sbuf) + uint32_t(uint64_t(r) * pitch - a0) + 3u * xmin;
+            // byte address (in shared memory) of my first source byte of row ra; rows are `pitch` apart
+            uint32_t src = smem_u32(sbuf) + uint32_t(uint64_t(ra) * pitch - a0) + 3u * xmin;
+            for (int r = ra; r < rb; ++r, src += uint32_t(pitch)) {
                 const uint32_t base = src & ~3u;
                 const uint32_t sh = (src & 3u) * 8u;
                 uint32_t w[NV + 1];
@@ -252,58 +308,16 @@ resize_bands_kernel(const ResizeParams p) {
                     acc1 += int32_t(__byte_perm(v[q1 >> 2], 0, 0x4440 | (q1 & 3))) * kh[t];
                     acc2 += int32_t(__byte_perm(v[q2 >> 2], 0, 0x4440 | (q2 & 3))) * kh[t];
                 }
-                uint8_t *dst = tmp + size_t(r - r0) * p.tmp_pitch + 3 * tid;
-                dst[0] = uint8_t(clip8(acc0));
-                dst[1] = uint8_t(clip8(acc1));
-                dst[2] = uint8_t(clip8(acc2));
+                uint8_t *dst = tmp + size_t((r - r0) & tmp_mask) * p.tmp_pitch + 3 * tid;
+                dst[0] = uint8_t(to_u8<kClip>(acc0));
+                dst[1] = uint8_t(to_u8<kClip>(acc1));
+                dst[2] = uint8_t(to_u8<kClip>(acc2));
             }
         }
-        __syncthreads();               // stage consumed (ring slot reusable), tmp rows visible
-    }
-
-    // ---- vertical pass out of the shared-memory intermediate -----------------------------
-    const int row_bytes = p.out_w * 3;
-    const int row_words = (row_bytes + 3) >> 2;
-    const uint32_t slot = p.out_slot ? p.out_slot[img] : uint32_t(img);
-    uint8_t *thumb = p.thumb + uint64_t(slot) * p.out_h * row_bytes;
-    float *prev = p.preview ? p.preview + uint64_t(slot) * 3 * p.out_h * p.out_w : nullptr;
-    const bool word_store = ((reinterpret_cast<uintptr_t>(thumb) | uint32_t(row_bytes)) & 3) == 0;
-    const int items = (oy1 - oy0) * row_words;
-    for (int it = tid; it < items; it += blockDim.x) {
-        const int ly = it / row_words;
-        const int wj = it - ly * row_words;
-        const int oy = oy0 + ly;
-        const int ymin = vb_s[2 * ly], cnt = vb_s[2 * ly + 1];
-        const int32_t *vk = vk_s + ly * p.ksize_v;
-        int32_t a0 = kRound, a1 = kRound, a2 = kRound, a3 = kRound;
-        const uint8_t *col = tmp + size_t(ymin - r0) * p.tmp_pitch + 4 * wj;
-        for (int t = 0; t < cnt; ++t) {
-            const uint32_t px = *reinterpret_cast<const uint32_t *>(col + size_t(t) * p.tmp_pitch);
-            const int32_t k = vk[t];
-            a0 += int32_t(px & 0xffu) * k;
-            a1 += int32_t((px >> 8) & 0xffu) * k;
-            a2 += int32_t((px >> 16) & 0xffu) * k;
-            a3 += int32_t(px >> 24) * k;
-        }
-        const uint32_t o[4] = {clip8(a0), clip8(a1), clip8(a2), clip8(a3)};
-        const int b_first = 4 * wj;
-        const int nb = min(4, row_bytes - b_first);
-        uint8_t *trow = thumb + size_t(oy) * row_bytes + b_first;
-        if (word_store && nb == 4) {
-            *reinterpret_cast<uint32_t *>(trow) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-        } else {
-            for (int i = 0; i < nb; ++i) trow[i] = uint8_t(o[i]);
-        }
-        if (prev) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i < nb) {
-                    const int b = b_first + i;
-                    const int px_x = b / 3, ch = b - 3 * px_x;
-                    prev[(size_t(ch) * p.out_h + oy) * p.out_w + px_x] = normalise(o[i], p.mean[ch], p.inv_std[ch]);
-                }
-            }
-        }
+        __syncthreads();               // stage consumed (ring slot reusable), intermediate rows visible
+        emit_ready(rb);
+        if (++buf == p.n_stages) { buf = 0; parity ^= 1u; }
+        if (++ibuf == p.n_stages) ibuf = 0;
     }
 }
 
@@ -394,36 +408,22 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
     if (pl->threads > 256) pl->ksh_bucket = 0;           // thread-per-column layout: out_w <= 256
     const int pitch = in_w * 3;
     pl->tmp_pitch = ((out_w * 3 + 15) / 16) * 16;
-    // stage: ~16 KB of rows; over-read padding = the widest register window + alignment slack
-    int rps = 16384 / pitch;
+    // stage: ~24 KB of rows (the per-stage barrier + refill costs ~80 instructions per thread, so a
+    // stage should hold several rows); over-read padding = the widest register window + alignment slack
+    int rps = 24576 / pitch;
     if (rps < 1) rps = 1;
     if (rps > 32) rps = 32;
     pl->rows_per_stage = rps;
     const int overread = 3 * 33 + 64;
     pl->stage_bytes = ((rps * pitch + 32 + overread + 127) / 128) * 128;
     pl->n_stages = 3;
-    // band height: intermediate tile <= ~48 KB, at least 1 row, at most 32
-    const size_t budget = 200 * 1024;
-    int best = 0;
-    for (int br = 32; br >= 1; --br) {
-        int max_rows = 0;
-        for (int oy0 = 0; oy0 < out_h; oy0 += br) {
-            const int oy1 = (oy0 + br < out_h ? oy0 + br : out_h) - 1;
-            const int rows = pl->v.bounds[2 * oy1] + pl->v.bounds[2 * oy1 + 1] - pl->v.bounds[2 * oy0];
-            if (rows > max_rows) max_rows = rows;
-        }
-        const size_t tile = size_t(max_rows) * pl->tmp_pitch;
-        const size_t total = size_t(pl->n_stages) * pl->stage_bytes + tile + size_t(br) * (2 + pl->v.ksize) * 4 + 64;
-        if ((tile <= 48 * 1024 || br == 1) && total <= budget) {
-            best = br;
-            pl->max_band_in_rows = max_rows;
-            pl->smem_bytes = total;
-            break;
-        }
-    }
-    if (best == 0) pl->ksh_bucket = 0;
-    pl->band_rows = best > 0 ? best : 1;
-    pl->n_bands = (out_h + pl->band_rows - 1) / pl->band_rows;
+    // rolling intermediate: a power-of-two ring that covers two stages plus one tap window
+    int ring_rows = 8;
+    while (ring_rows < 2 * rps + pl->v.ksize + 2) ring_rows <<= 1;
+    pl->tmp_ring_rows = ring_rows;
+    pl->smem_fixed = size_t(pl->n_stages) * pl->stage_bytes + size_t(ring_rows) * pl->tmp_pitch + 64;
+    pl->smem_max = pl->smem_fixed + size_t(out_h) * (2 + pl->v.ksize) * 4;
+    if (pl->smem_max > 220 * 1024) pl->ksh_bucket = 0;       // does not fit: generic kernel
     *plan_out = pl;
     return B2_OK;
 }
@@ -469,15 +469,27 @@ extern "C" int b2_resize_normalize_batch(const b2_resize_plan *pl, const uint8_t
     p.hbounds = pl->d_hbounds; p.hcoeffs = pl->d_hcoeffs; p.vbounds = pl->d_vbounds; p.vcoeffs = pl->d_vcoeffs;
     p.in_h = pl->in_h; p.in_w = pl->in_w; p.out_h = pl->out_h; p.out_w = pl->out_w;
     p.ksize_h = pl->h.ksize; p.ksize_v = pl->v.ksize;
-    p.band_rows = pl->band_rows; p.n_bands = pl->n_bands; p.max_band_in_rows = pl->max_band_in_rows;
+    // Bands: the whole image per CTA when the batch alone fills the GPU (no input row is read twice);
+    // small batches are cut into bands of >= 16 output rows so that every SM gets work.
+    int n_bands = 1;
+    {
+        const int want_ctas = 4 * sm_count();
+        if (int64_t(n) < want_ctas) n_bands = int((want_ctas + n - 1) / n);
+        const int max_bands = pl->out_h / 16 > 0 ? pl->out_h / 16 : 1;
+        if (n_bands > max_bands) n_bands = max_bands;
+    }
+    p.band_rows = (pl->out_h + n_bands - 1) / n_bands;
+    p.n_bands = (pl->out_h + p.band_rows - 1) / p.band_rows;
+    p.max_band_in_rows = 0;
     p.rows_per_stage = pl->rows_per_stage; p.stage_bytes = pl->stage_bytes; p.n_stages = pl->n_stages;
-    p.tmp_pitch = pl->tmp_pitch;
+    p.tmp_pitch = pl->tmp_pitch; p.tmp_ring_rows = pl->tmp_ring_rows;
+    const size_t smem_launch = pl->smem_fixed + size_t(p.band_rows) * (2 + pl->v.ksize) * 4;
     for (int c = 0; c < 3; ++c) {
         p.mean[c] = mean ? mean[c] : 0.0f;
         p.inv_std[c] = inv_std ? inv_std[c] : 1.0f;
     }
     const bool fast = pl->ksh_bucket != 0 && resize_path_override() != 1 &&
-                      uint64_t(n) * uint64_t(pl->n_bands) < 0x7fffffffull;
+                      uint64_t(n) * uint64_t(p.n_bands) < 0x7fffffffull;
     if (!fast) {
         const uint64_t threads = uint64_t(n) * pl->out_h * pl->out_w;
         B2_REQUIRE((threads + 255) / 256 < 0x7fffffffull, "b2_resize_normalize_batch: batch too large");
@@ -496,28 +508,28 @@ extern "C" int b2_resize_normalize_batch(const b2_resize_plan *pl, const uint8_t
             case 17: bi = 4; break; case 25: bi = 5; break; default: bi = 6; break;
         }
         const int dev = pl->device & 63;
-        if (attr_bytes[dev][bi] < pl->smem_bytes) {
+        if (attr_bytes[dev][bi] < pl->smem_max) {
             switch (pl->ksh_bucket) {
-                case 3: e = set_smem_attr<3>(pl->smem_bytes); break;
-                case 5: e = set_smem_attr<5>(pl->smem_bytes); break;
-                case 9: e = set_smem_attr<9>(pl->smem_bytes); break;
-                case 13: e = set_smem_attr<13>(pl->smem_bytes); break;
-                case 17: e = set_smem_attr<17>(pl->smem_bytes); break;
-                case 25: e = set_smem_attr<25>(pl->smem_bytes); break;
-                default: e = set_smem_attr<33>(pl->smem_bytes); break;
+                case 3: e = set_smem_attr<3>(pl->smem_max); break;
+                case 5: e = set_smem_attr<5>(pl->smem_max); break;
+                case 9: e = set_smem_attr<9>(pl->smem_max); break;
+                case 13: e = set_smem_attr<13>(pl->smem_max); break;
+                case 17: e = set_smem_attr<17>(pl->smem_max); break;
+                case 25: e = set_smem_attr<25>(pl->smem_max); break;
+                default: e = set_smem_attr<33>(pl->smem_max); break;
             }
-            if (e == cudaSuccess) attr_bytes[dev][bi] = pl->smem_bytes;
+            if (e == cudaSuccess) attr_bytes[dev][bi] = pl->smem_max;
         }
     }
     B2_CUDA_CHECK(e);
     switch (pl->ksh_bucket) {
-        case 3: launch_bands<3>(p, n, pl->threads, pl->smem_bytes, st); break;
-        case 5: launch_bands<5>(p, n, pl->threads, pl->smem_bytes, st); break;
-        case 9: launch_bands<9>(p, n, pl->threads, pl->smem_bytes, st); break;
-        case 13: launch_bands<13>(p, n, pl->threads, pl->smem_bytes, st); break;
-        case 17: launch_bands<17>(p, n, pl->threads, pl->smem_bytes, st); break;
-        case 25: launch_bands<25>(p, n, pl->threads, pl->smem_bytes, st); break;
-        default: launch_bands<33>(p, n, pl->threads, pl->smem_bytes, st); break;
+        case 3: launch_bands<3>(p, n, pl->threads, smem_launch, st); break;
+        case 5: launch_bands<5>(p, n, pl->threads, smem_launch, st); break;
+        case 9: launch_bands<9>(p, n, pl->threads, smem_launch, st); break;
+        case 13: launch_bands<13>(p, n, pl->threads, smem_launch, st); break;
+        case 17: launch_bands<17>(p, n, pl->threads, smem_launch, st); break;
+        case 25: launch_bands<25>(p, n, pl->threads, smem_launch, st); break;
+        default: launch_bands<33>(p, n, pl->threads, smem_launch, st); break;
     }
     B2_LAUNCH_CHECK("resize_bands_kernel");
     return B2_OK;

@@ -57,10 +57,19 @@ class IngestPipeline:
         self.copy_stream = torch.cuda.Stream(dev)
         self.hash_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
         self.resize_streams = [torch.cuda.Stream(dev) for _ in range(2)]
+        self.final_stream = torch.cuda.Stream(dev)            # joins the others; private, so pipelines do not serialise
         self.kernel_launches = 0
 
     def run(self, host_images: torch.Tensor, existing_sorted: Optional[torch.Tensor] = None) -> PipelineResult:
-        """host_images: pinned uint8 [n, in_h*in_w*3] (raw RGB HWC = the synthetic "file bytes")."""
+        """Blocking form: submit + result."""
+        self.submit(host_images, existing_sorted)
+        return self.result()
+
+    def submit(self, host_images: torch.Tensor, existing_sorted: Optional[torch.Tensor] = None) -> None:
+        """Enqueue the whole batch (copies, kernels, read-backs) without waiting for the GPU.
+        host_images: pinned uint8 [n, in_h*in_w*3] (raw RGB HWC = the synthetic "file bytes").
+        A service keeps two pipelines and submits batch i+1 before asking for result i, so the hash
+        tail of one batch hides under the copies of the next."""
         n = host_images.shape[0]
         assert n <= self.max_images and host_images.is_pinned() and host_images.dtype == torch.uint8
         main = torch.cuda.current_stream(self.dev)
@@ -98,15 +107,24 @@ class IngestPipeline:
                 if prev is not None:
                     self.h_prev[lo:hi].copy_(prev, non_blocking=True)
                     d2h += prev.numel() * 4
+        fin = self.final_stream
         for s in [self.copy_stream] + self.hash_streams + self.resize_streams:
-            main.wait_stream(s)
-        is_new, first, last, counts = engine.dedupe_device(self.d_digests[:n], existing_sorted=existing_sorted)
-        self.kernel_launches += 2
-        self.h_digests[:n].copy_(self.d_digests[:n], non_blocking=True)
-        self.h_is_new[:n].copy_(is_new, non_blocking=True)
-        self.h_counts.copy_(counts, non_blocking=True)
-        d2h += n * 33 + 12
-        main.synchronize()
+            fin.wait_stream(s)
+        with torch.cuda.stream(fin):
+            is_new, first, last, counts = engine.dedupe_device(self.d_digests[:n], existing_sorted=existing_sorted)
+            self.kernel_launches += 2
+            self.h_digests[:n].copy_(self.d_digests[:n], non_blocking=True)
+            self.h_is_new[:n].copy_(is_new, non_blocking=True)
+            self.h_counts.copy_(counts, non_blocking=True)
+            d2h += n * 33 + 12
+            self._done = torch.cuda.Event()
+            self._done.record(fin)
+        self._pending = (n, h2d, d2h)
+
+    def result(self) -> PipelineResult:
+        """Wait for the submitted batch and hand back the pinned host results."""
+        n, h2d, d2h = self._pending
+        self._done.synchronize()
         c = self.h_counts.tolist()
         return PipelineResult(self.h_digests[:n], self.h_is_new[:n],
                               {"processed": c[0], "created": c[1], "updated": c[2]},
