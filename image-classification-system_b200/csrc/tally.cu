@@ -522,6 +522,313 @@ tally_warp_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
     if (threadIdx.x < 7 && s_tot[256 + threadIdx.x]) atomicAdd(&g_partials[k + threadIdx.x], s_tot[256 + threadIdx.x]);
 }
 
+// ----------------------------------------------------------------------------------------
+// tally_image_kernel — thread-per-image formulation for rows ordered by image_idx.
+// The warp kernel above spends ~108 warp-instructions per 32 rows because the whole warp cooperates on
+// each row group.  Here every THREAD tallies a whole image by itself, so the SIMT width is used on
+// independent rows: ~10 thread-instructions per row.
+//   * CTA b owns the images that START in its nominal row range (same rule as above) and walks them in
+//     tiles of `tile_images` images whose counters (int32, row pitch k|1 so a column walk is
+//     conflict-free) live in shared memory.
+//   * Phase A (coalesced): blocks of 4096 rows, 16 consecutive rows per thread (six 128-bit loads).
+//     Each row becomes ONE byte in a shared row buffer — its class, or 0xFF when inactive / foreign /
+//     out of range — and every image change records where the image's rows start and end in that
+//     buffer.  Order and range checks happen here.  A phase ends when the buffer is full or the stream
+//     leaves the tile.
+//   * Phase B: thread i walks the rows [start_i, end_i) of image tile_base+i in the row buffer and
+//     increments its own counters with plain read-modify-writes: no atomics, no warp collectives.
+//   * A finished tile is written to d_counts with coalesced stores and folded into the integer
+//     partials exactly like the other kernels.
+// ----------------------------------------------------------------------------------------
+constexpr int kImgThreads = 256;
+constexpr int kImgBlockRows = kImgThreads * kRowsPerThread;       // 4096
+constexpr uint32_t kNoRow = 0xffffffffu;
+
+struct ImgSmem {
+    int32_t *cnt;                 // tile_images * pitch
+    uint8_t *rowbuf;              // cap_rows
+    uint32_t *seg_start, *seg_end;// tile_images each
+    unsigned long long *class_tot;// k
+    unsigned long long *part;     // 8
+    uint32_t *first_beyond;       // 1 (row offset in the buffer of the first row past the tile)
+    uint32_t *tile_tot;           // k (class totals of the open tile, 32-bit)
+};
+__host__ __device__ inline size_t img_smem_layout(uint32_t tile_images, uint32_t pitch, uint32_t cap_rows, uint32_t k,
+                                                  size_t *o_rowbuf, size_t *o_seg, size_t *o_tot) {
+    size_t off = (size_t(tile_images) * pitch * 4 + 15) & ~size_t(15);
+    *o_rowbuf = off; off += (size_t(cap_rows) + 15) & ~size_t(15);
+    *o_seg = off; off += size_t(tile_images) * 8;
+    off = (off + 7) & ~size_t(7);
+    *o_tot = off; off += size_t(k) * 8 + 8 * 8 + 16 + size_t(k) * 4;
+    return off;
+}
+
+__global__ void __launch_bounds__(kImgThreads, 3)
+tally_image_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
+                   const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
+                   uint32_t k, uint32_t tile_images, uint32_t cap_rows, int32_t *__restrict__ counts,
+                   unsigned long long *__restrict__ g_partials) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t pitch = k | 1u;
+    size_t o_rowbuf, o_seg, o_tot;
+    img_smem_layout(tile_images, pitch, cap_rows, k, &o_rowbuf, &o_seg, &o_tot);
+    ImgSmem sm;
+    sm.cnt = reinterpret_cast<int32_t *>(smem_raw);
+    sm.rowbuf = smem_raw + o_rowbuf;
+    sm.seg_start = reinterpret_cast<uint32_t *>(smem_raw + o_seg);
+    sm.seg_end = sm.seg_start + tile_images;
+    sm.class_tot = reinterpret_cast<unsigned long long *>(smem_raw + o_tot);
+    sm.part = sm.class_tot + k;
+    sm.first_beyond = reinterpret_cast<uint32_t *>(sm.part + 8);
+    sm.tile_tot = sm.first_beyond + 4;
+    const uint32_t tid = threadIdx.x;
+
+    const uint32_t G = gridDim.x, b = blockIdx.x;
+    const int32_t img_end_all = image_base + int32_t(n_images);
+    auto nominal = [&](uint64_t i) -> uint64_t {
+        return i >= G ? rows : (((rows / G) * i + (rows % G) * i / G) & ~uint64_t(kRowsPerThread - 1));
+    };
+    const uint64_t nom0 = nominal(b), nom1 = nominal(b + 1);
+    auto boundary = [&](uint64_t nom) -> int32_t {
+        const int32_t v = __ldg(image_idx + nom);
+        return v < image_base ? image_base : (v >= img_end_all - 1 ? img_end_all : v + 1);
+    };
+    int32_t I0, I1;
+    if (rows == 0) {
+        I0 = image_base + int32_t(uint64_t(n_images) * b / G);
+        I1 = image_base + int32_t(uint64_t(n_images) * (b + 1) / G);
+    } else {
+        I0 = b == 0 ? image_base : boundary(nom0);
+        I1 = b + 1 == G ? img_end_all : boundary(nom1);
+        if (I1 < I0) I1 = I0;
+    }
+
+    for (uint32_t e = tid; e < tile_images * pitch; e += blockDim.x) sm.cnt[e] = 0;
+    for (uint32_t i = tid; i < tile_images; i += blockDim.x) { sm.seg_start[i] = 0; sm.seg_end[i] = 0; }
+    for (uint32_t c = tid; c < k + 8; c += blockDim.x) sm.class_tot[c] = 0;
+    for (uint32_t c = tid; c < k; c += blockDim.x) sm.tile_tot[c] = 0;
+    if (tid == 0) *sm.first_beyond = kNoRow;
+    __syncthreads();
+
+    uint32_t seen = 0, unsorted = 0;
+    int32_t tb = I0;                                                         // first image of the open tile
+    int32_t tile_end = I1 - tb > int32_t(tile_images) ? tb + int32_t(tile_images) : I1;
+
+    // write the open tile, fold it into the partials, zero it, open the next one (uniform)
+    auto flush = [&]() {
+        __syncthreads();
+        const uint32_t n_img = uint32_t(tile_end - tb);
+        int32_t *dst = counts + size_t(tb - image_base) * k;
+        unsigned long long s2 = 0;
+        // element order: coalesced stores, class totals, sum of squares
+        uint32_t i = tid / k, c = tid - i * k;
+        const uint32_t di = blockDim.x / k, dc = blockDim.x - di * k;
+        for (uint32_t e = tid; e < n_img * k; e += blockDim.x) {
+            const uint32_t v = uint32_t(sm.cnt[i * pitch + c]);
+            dst[e] = int32_t(v);
+            if (v) {
+                s2 += (unsigned long long)v * v;
+                atomicAdd(&sm.tile_tot[c], v);                              // native 32-bit shared atomic; a tile holds < 2^32 ratings
+            }
+            i += di; c += dc;
+            if (c >= k) { c -= k; ++i; }
+        }
+        // one thread per image: n_i and what derives from it (pitch is odd: conflict-free)
+        unsigned long long r = 0, pairs = 0, rated = 0, pair_images = 0;
+        for (uint32_t im = tid; im < n_img; im += blockDim.x) {
+            const int32_t *row = sm.cnt + im * pitch;
+            unsigned long long n = 0;
+            for (uint32_t j = 0; j < k; ++j) n += uint32_t(row[j]);
+            r += n; rated += n >= 1; pair_images += n >= 2; pairs += n * (n - (n > 0));
+        }
+        part_add(sm.part, P_S2, s2);
+        part_add(sm.part, P_R, r);
+        part_add(sm.part, P_RATED, rated);
+        part_add(sm.part, P_PAIR_IMAGES, pair_images);
+        part_add(sm.part, P_PAIRS, pairs);
+        __syncthreads();
+        for (uint32_t c2 = tid; c2 < k; c2 += blockDim.x) {                  // fold the tile's class totals into 64 bits
+            sm.class_tot[c2] += sm.tile_tot[c2];
+            sm.tile_tot[c2] = 0;
+        }
+        for (uint32_t e = tid; e < n_img * pitch; e += blockDim.x) sm.cnt[e] = 0;
+        tb = tile_end;
+        tile_end = I1 - tb > int32_t(tile_images) ? tb + int32_t(tile_images) : I1;
+        __syncthreads();
+    };
+
+    uint64_t consume_from = nom0;                                            // first row not yet tallied (uniform)
+    bool stream_done = rows == 0 || nom0 >= rows;
+    while (!stream_done) {
+        // ---------------- phase A: fill the row buffer ----------------
+        const uint64_t buf_row0 = consume_from & ~uint64_t(kRowsPerThread - 1);
+        // number of 4096-row blocks this phase may buffer (uniform), and where they end
+        uint32_t n_blk = cap_rows / kImgBlockRows;
+        {
+            const uint64_t left = (rows - buf_row0 + kImgBlockRows - 1) / kImgBlockRows;
+            if (left < n_blk) n_blk = uint32_t(left);
+        }
+        const uint64_t loaded_end = buf_row0 + uint64_t(n_blk) * kImgBlockRows < rows
+                                        ? buf_row0 + uint64_t(n_blk) * kImgBlockRows : rows;
+        auto process = [&](const RowBlock &rbk, uint64_t row0) {
+            const int32_t ii[16] = {rbk.idx[0].x, rbk.idx[0].y, rbk.idx[0].z, rbk.idx[0].w, rbk.idx[1].x, rbk.idx[1].y,
+                                    rbk.idx[1].z, rbk.idx[1].w, rbk.idx[2].x, rbk.idx[2].y, rbk.idx[2].z, rbk.idx[2].w,
+                                    rbk.idx[3].x, rbk.idx[3].y, rbk.idx[3].z, rbk.idx[3].w};
+            const uint32_t cw[4] = {rbk.cls.x, rbk.cls.y, rbk.cls.z, rbk.cls.w};
+            const uint32_t aw[4] = {rbk.act.x, rbk.act.y, rbk.act.z, rbk.act.w};
+            int32_t prev = (row0 > 0 && row0 <= rows) ? __ldg(image_idx + row0 - 1) : INT32_MIN;
+            uint32_t packed[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+            const uint32_t off0 = uint32_t(row0 - buf_row0);
+            // Common path: all 16 rows exist, are new to this phase and lie in the open tile (rows are ordered,
+            // so the first and the last decide).  The 16 class bytes are merged with the active / range masks
+            // four at a time; image changes are rare (one per ~100 rows), so each row costs one compare and a
+            // short, rarely taken block that records where the images start and end in the row buffer.  Only
+            // threads at the edges of a phase or of a tile take the general path below: divergence is
+            // confined to the one or two warps that hold such an edge.
+            if (row0 > consume_from && row0 + kRowsPerThread <= rows && ii[0] >= tb && ii[15] < tile_end &&
+                prev <= ii[0]) {
+                const uint32_t n_tile = uint32_t(tile_end - tb);
+                const uint32_t k4 = k >= 256 ? 0u : k * 0x01010101u;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t in_range = k >= 256 ? 0xffffffffu : __vcmpltu4(cw[w], k4);
+                    const uint32_t keep = in_range & __vcmpne4(aw[w], 0u);
+                    packed[w] = (cw[w] & keep) | ~keep;
+                    seen += __popc(in_range) >> 3;
+                }
+                *reinterpret_cast<uint4 *>(sm.rowbuf + off0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                const bool count_order = row0 + kRowsPerThread <= nom1;      // nom1 is 16-aligned: all rows or none
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int32_t img = ii[j];
+                    if (img != prev) {
+                        if (count_order) unsorted += img < prev;
+                        const uint32_t rel = uint32_t(img - tb), relp = uint32_t(prev - tb);
+                        if (rel < n_tile) sm.seg_start[rel] = off0 + j;
+                        if (relp < n_tile) sm.seg_end[relp] = off0 + j;
+                    }
+                    prev = img;
+                }
+                return;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint64_t row = row0 + j;
+                const int32_t img = ii[j];
+                const bool valid = row < rows && row >= consume_from;        // exists and not tallied in an earlier phase
+                const uint32_t c = (cw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                const uint32_t a = (aw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                if (valid) {
+                    if (row < nom1) unsorted += img < prev;                  // pairs (r-1, r), nom0 <= r < nom1
+                    const bool in_tile = (img >= tb) & (img < tile_end);
+                    const bool first_here = (img != prev) | (row == consume_from);
+                    if (in_tile) {
+                        seen += c < k;
+                        if (a && c < k) packed[j >> 2] = (packed[j >> 2] & ~(0xffu << (8 * (j & 3)))) | (c << (8 * (j & 3)));
+                        if (first_here) sm.seg_start[img - tb] = off0 + j;
+                    } else if (img >= tile_end && first_here && (prev < tile_end || row == consume_from)) {
+                        atomicMin(sm.first_beyond, off0 + j);                // the stream leaves the tile here
+                    }
+                    if (img != prev && row > consume_from && prev >= tb && prev < tile_end)
+                        sm.seg_end[prev - tb] = off0 + j;                    // the previous image's rows end here
+                }
+                prev = img;
+            }
+            *reinterpret_cast<uint4 *>(sm.rowbuf + off0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        };
+        // Software pipeline: the loads of block nb+1 are in flight while block nb is scanned; no barrier
+        // between blocks.  Rows are ordered, so the image of a block's LAST row tells every thread alike
+        // whether the stream leaves the tile inside that block: if it does, nothing further is loaded.
+        {
+            RowBlock q[2];
+            const uint64_t trow = uint64_t(tid) * kRowsPerThread;
+            auto last_img_of = [&](uint32_t cb) -> int32_t {
+                const uint64_t end = buf_row0 + uint64_t(cb + 1) * kImgBlockRows;
+                return __ldg(image_idx + (end < rows ? end : rows) - 1);
+            };
+            int32_t last_img = 0, next_last = 0;
+            if (n_blk) { load_rows(q[0], image_idx, class_idx, active, buf_row0 + trow, rows); last_img = last_img_of(0); }
+            for (uint32_t nb = 0; nb < n_blk; nb += 2) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t cb = nb + u;
+                    if (cb < n_blk) {
+                        const uint64_t blk = buf_row0 + uint64_t(cb) * kImgBlockRows;
+                        const bool more = cb + 1 < n_blk && last_img < tile_end;
+                        if (more) {
+                            load_rows(q[u ^ 1], image_idx, class_idx, active, blk + kImgBlockRows + trow, rows);
+                            next_last = last_img_of(cb + 1);
+                        }
+                        process(q[u], blk + trow);
+                        last_img = next_last;
+                        if (!more) nb = n_blk;                               // leave both loops after this block
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t fb = *sm.first_beyond;
+        const uint64_t stop = fb != kNoRow ? buf_row0 + fb : loaded_end;     // first row NOT tallied by this phase
+        if (tid == 0 && stop > consume_from) {                               // close the last image of the buffer
+            const int32_t li = __ldg(image_idx + stop - 1);
+            if (li >= tb && li < tile_end) sm.seg_end[li - tb] = uint32_t(stop - buf_row0);
+        }
+        __syncthreads();
+        // ---------------- phase B: one thread per image ----------------
+        const uint32_t n_tile = uint32_t(tile_end - tb);
+        for (uint32_t im = tid; im < n_tile; im += blockDim.x) {
+            const uint32_t s = sm.seg_start[im], e = sm.seg_end[im];
+            int32_t *my = sm.cnt + im * pitch;
+            uint32_t r = s;
+            for (; r + 4 <= e; r += 4) {          // four row bytes first, then the counter updates: the loads
+                const uint32_t m0 = sm.rowbuf[r], m1 = sm.rowbuf[r + 1], m2 = sm.rowbuf[r + 2], m3 = sm.rowbuf[r + 3];
+                if (m0 != 0xffu) my[m0] += 1;     // do not wait behind the stores
+                if (m1 != 0xffu) my[m1] += 1;
+                if (m2 != 0xffu) my[m2] += 1;
+                if (m3 != 0xffu) my[m3] += 1;
+            }
+            for (; r < e; ++r) {
+                const uint32_t m = sm.rowbuf[r];
+                if (m != 0xffu) my[m] += 1;
+            }
+            sm.seg_start[im] = 0;
+            sm.seg_end[im] = 0;
+        }
+        if (tid == 0) *sm.first_beyond = kNoRow;
+        consume_from = stop;
+        // the tile is complete when the stream left it (or ended); the stream is over for this CTA when it
+        // ended or when the next row belongs to somebody else's images
+        const bool left_tile = fb != kNoRow || stop >= rows;
+        bool next_foreign = stop >= rows;
+        if (!next_foreign && fb != kNoRow) next_foreign = __ldg(image_idx + stop) >= I1;
+        if (left_tile) {
+            if (tb < I1) flush(); else __syncthreads();
+            if (!next_foreign) {                                             // tiles without any row: write zeros, no reload
+                const int32_t ni = __ldg(image_idx + stop);
+                while (tb < I1 && ni >= tile_end) flush();
+            }
+            if (next_foreign) {
+                // order check still has to reach nom1 when this CTA's images end early (unsorted input only)
+                stream_done = true;
+            } else if (tb >= I1) {
+                stream_done = true;
+            }
+        } else {
+            __syncthreads();
+        }
+    }
+    // remaining tiles (image ranges without rows), then the order check of rows this CTA did not stream
+    while (tb < I1) flush();
+    for (uint64_t r = (consume_from > nom0 ? consume_from : nom0) + tid; r < nom1 && r < rows; r += blockDim.x) {
+        const int32_t prev = r > 0 ? __ldg(image_idx + r - 1) : INT32_MIN;
+        unsorted += __ldg(image_idx + r) < prev;
+    }
+    part_add(sm.part, P_ROWS_SEEN, seen);
+    part_add(sm.part, P_UNSORTED, unsorted);
+    __syncthreads();
+    commit_partials(sm.part, sm.class_tot, k, g_partials);
+}
+
 // Any row order: one RED.ADD per active row into a zeroed count matrix.
 __global__ void __launch_bounds__(256)
 tally_scatter_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
@@ -619,10 +926,10 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
 
 }  // namespace b2
 
-// B2_TALLY_PATH: 0 = auto (warp kernel), 1 = shared-memory tile kernel (comparison).
+// B2_TALLY_PATH: unset = auto, 0 = thread-per-image kernel, 1 = MATCH.ANY warp kernel, 2 = shared-atomic tile kernel.
 static int tally_path_override() {
     const char *e = getenv("B2_TALLY_PATH");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : -1;
 }
 
 extern "C" uint64_t b2_label_tally_workspace_bytes(uint32_t n_images) {
@@ -656,7 +963,38 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
     const uint32_t tile_images = pick_tile_images(k);
     const size_t smem = tally_smem_bytes(tile_images, k);
     if (flags & B2_TALLY_SORTED) {
-        if (tally_path_override() == 1) {                    // shared-memory tile kernel (comparison only)
+        // Auto: a thread per image needs many images per buffer phase, so images with very many rows go to the
+        // warp kernel (whose common case is "32 rows of the same image"); everything else to the image kernel.
+        int path = tally_path_override();
+        if (path < 0) path = (rows / n_images >= 512) ? 1 : 0;
+        if (path == 0) {                                     // thread-per-image kernel
+            const uint32_t pitch = k | 1u;
+            uint32_t ti = 192, cap = 20480;                 // 39 KB counters (k = 50) + 20 KB rows: three CTAs per SM
+            if (const char *e = getenv("B2_TALLY_TILE")) ti = uint32_t(atoi(e));
+            if (const char *e = getenv("B2_TALLY_CAP")) cap = uint32_t(atoi(e));
+            const uint32_t by_smem = (56u * 1024u) / (pitch * 4u);           // counters <= 56 KB
+            if (ti > by_smem) ti = by_smem;
+            if (ti < 1) ti = 1;
+            cap = cap / kImgBlockRows * kImgBlockRows;
+            if (cap < uint32_t(kImgBlockRows)) cap = kImgBlockRows;
+            size_t o1, o2, o3;
+            const size_t smem_img = img_smem_layout(ti, pitch, cap, k, &o1, &o2, &o3);
+            B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_image_kernel), smem_img));
+            int per_sm = int((220u * 1024u) / (smem_img + 1024));
+            if (per_sm > 4) per_sm = 4;
+            if (per_sm < 1) per_sm = 1;
+            uint64_t want = rows ? (rows + 4ull * kImgBlockRows - 1) / (4ull * kImgBlockRows)
+                                 : (uint64_t(n_images) + ti - 1) / ti;
+            const uint64_t cap_ctas = uint64_t(per_sm) * uint64_t(sm_count());
+            if (want > cap_ctas) want = cap_ctas;
+            if (want < 1) want = 1;
+            tally_image_kernel<<<uint32_t(want), kImgThreads, smem_img, st>>>(d_image_idx, d_class_idx, d_active, rows,
+                                                                             int32_t(image_base), n_images, k, ti, cap,
+                                                                             d_counts, partials);
+            B2_LAUNCH_CHECK("tally_image_kernel");
+            return B2_OK;
+        }
+        if (path == 2) {                                     // shared-memory-atomic tile kernel (comparison only)
             B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_sorted_kernel), smem));
             uint64_t want = (rows + 4ull * kBlockRows - 1) / (4ull * kBlockRows);
             const uint64_t by_images = (uint64_t(n_images) + tile_images - 1) / tile_images;

@@ -24,11 +24,16 @@ def _compare(img, cls, act, n_images, k, sorted_by_image, image_base=0):
 
 
 @pytest.mark.parametrize("n_images,k,n_raters", [(1000, 50, 10), (1, 1, 1), (37, 3, 5), (5000, 50, 100),
-                                                 (300, 255, 7), (100_000, 50, 20), (2049, 17, 33)])
-@pytest.mark.parametrize("mode", ["sorted", "scatter"])
-def test_synthetic_rows(n_images, k, n_raters, mode):
+                                                 (300, 255, 7), (100_000, 50, 20), (2049, 17, 33), (40, 50, 3000)])
+@pytest.mark.parametrize("mode", ["sorted", "sorted-image-kernel", "sorted-warp-kernel", "sorted-tile-kernel", "scatter"])
+def test_synthetic_rows(n_images, k, n_raters, mode, monkeypatch):
+    """Every sorted-mode kernel (auto choice, thread-per-image, MATCH.ANY warp, shared-atomic tile) and the
+    any-order kernel against the oracle, bit-exact."""
+    path = {"sorted-image-kernel": "0", "sorted-warp-kernel": "1", "sorted-tile-kernel": "2"}.get(mode)
+    if path is not None:
+        monkeypatch.setenv("B2_TALLY_PATH", path)
     img, cls, act = synth_label_rows(n_images, k, n_raters, shuffled=(mode == "scatter"))
-    res, p = _compare(img, cls, act, n_images, k, sorted_by_image=(mode == "sorted"))
+    res, p = _compare(img, cls, act, n_images, k, sorted_by_image=(mode != "scatter"))
     if n_raters > 1 and p["R"] > 0:
         # constant-n formula on the same integers: bit-identical float64
         assert res.kappa(n_images, n_raters) == fleiss_kappa(p["class_totals"], p["S2"], p["R"], n_images, n_raters)
