@@ -829,6 +829,313 @@ tally_image_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restr
     commit_partials(sm.part, sm.class_tot, k, g_partials);
 }
 
+// ----------------------------------------------------------------------------------------
+// tally_slab_kernel — the product kernel for rows ordered by image_idx: a thread per ROW, lanes of a warp
+// a whole slab (132 rows) apart, shared-memory atomics into a sliding window of images.
+//   * CTA b owns the images that START in its nominal row range (same rule as the kernels above) and
+//     streams stages of 4224 rows (32 slabs x 132) through a 3-deep shared-memory ring filled by the
+//     bulk-copy (TMA) engine: three 1-D copies per stage (image_idx, class_idx, active) issued by one
+//     thread, completion on an mbarrier, so up to two stages per CTA are in flight while one is tallied.
+//   * Lane l of every warp reads slab l of the stage; warp w takes quads [33w/8, 33(w+1)/8) of each slab.
+//     A quad is 4 consecutive rows: one LDS.128 of image indices plus one LDS.32 each of class and active
+//     bytes.  The slab pitch is 33 quads = 1 (mod 32) 16-byte units / 4-byte words, so both loads are
+//     bank-conflict free without padding the TMA destination.  Lanes that are 132 rows apart sit in
+//     different images (BASELINE config 4 has ~100 rows per image), hence no same-address atomics
+//     inside a warp instruction; with larger images the atomics serialise but stay correct.
+//   * Counters live in a ring of T = 2^t images (slot = image & (T-1)): images below the first image of
+//     the current stage are complete (rows are ordered) and are flushed only when the stage would not
+//     fit in the window, so a stage is normally tallied exactly once.  A stage spanning more than T
+//     images is re-scanned window by window, jumping over image gaps.
+//   * Flush: a warp per image, a lane per class — conflict-free LDS, 4k-byte contiguous stores,
+//     class totals in registers, n_i with one REDUX.  Images without rows are zero-filled on the way,
+//     so d_counts needs no memset.  Partials and checks exactly as in the kernels above.
+// ----------------------------------------------------------------------------------------
+constexpr int kSlabQuads = 33;                                    // quads per slab: = 1 (mod 32)
+constexpr int kSlabRows = 4 * kSlabQuads;                         // 132
+constexpr int kSlabStageRows = 32 * kSlabRows;                    // 4224 (multiple of 16: TMA alignment)
+constexpr int kSlabStageBytes = kSlabStageRows * 6;               // 25 344
+constexpr int kSlabStages = 3;
+constexpr int kSlabThreads = 256;
+constexpr int kSlabWarps = kSlabThreads / 32;
+
+__host__ __device__ inline size_t slab_smem_bytes(uint32_t tile_images, uint32_t k) {
+    return size_t(kSlabStages) * kSlabStageBytes + ((size_t(tile_images) * k * 4 + 15) & ~size_t(15)) + 1024 +
+           size_t(k) * 8 + 8 * 8 + 16 + kSlabStages * 8;
+}
+
+// One row of a quad, branch-free: in the window and class in range => seen++; also active => one shared
+// RED.ADD on the counter of (image & tmask, class).  Eleven instructions; written in PTX so that the atomic
+// is unconditional: ptxas turns every predicated shared atomic into BSSY / BRA / BSYNC, and a literal 1 into
+// ATOMS.POPC.INC, so the increment is a register holding 1 or 0.  The address is always inside the tile plus
+// its 1 KB pad (slot < T, class byte < 256), so rows that do not count simply add 0.  No "memory" clobber on purpose: the counters are only read
+// after a __syncthreads(), and the clobber would stop the next quad's loads from being hoisted.
+template <int J>
+__device__ __forceinline__ void slab_row(int32_t img, uint32_t cw, uint32_t aw, int32_t tb, uint32_t span, uint32_t k,
+                                         uint32_t tmask, uint32_t k4, uint32_t tile_s, uint32_t one, uint32_t &seen) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b32 d, c, a, t;\n\t"
+        "sub.u32 d, %1, %2;\n\t"
+        "setp.lt.u32 p, d, %3;\n\t"
+        "prmt.b32 c, %4, 0, %5;\n\t"
+        "setp.lt.and.u32 p, c, %6, p;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t"
+        "and.b32 a, %7, %8;\n\t"
+        "setp.ne.and.u32 q, a, 0, p;\n\t"
+        "and.b32 t, %1, %9;\n\t"
+        "mad.lo.u32 t, t, %10, %11;\n\t"
+        "mad.lo.u32 t, c, 4, t;\n\t"
+        "selp.u32 a, %12, 0, q;\n\t"
+        "red.shared.add.u32 [t], a;\n\t"
+        "}"
+        : "+r"(seen)
+        : "r"(img), "r"(tb), "r"(span), "r"(cw), "n"(0x4440 + J), "r"(k), "r"(aw), "n"(0xffu << (8 * J)), "r"(tmask),
+          "r"(k4), "r"(tile_s), "r"(one));
+}
+
+template <int KC>                                                 // KC = ceil(k / 32)
+__global__ void __launch_bounds__(kSlabThreads, 2)
+tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
+                  const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
+                  uint32_t k, uint32_t tile_log2, int32_t *__restrict__ counts,
+                  unsigned long long *__restrict__ g_partials) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t T = 1u << tile_log2, tmask = T - 1u;
+    uint8_t *ring = smem_raw;
+    int32_t *tile = reinterpret_cast<int32_t *>(smem_raw + size_t(kSlabStages) * kSlabStageBytes);
+    unsigned long long *class_tot = reinterpret_cast<unsigned long long *>(
+        reinterpret_cast<uint8_t *>(tile) + ((size_t(T) * k * 4 + 15) & ~size_t(15)) + 1024);   // pad: see slab_row
+    unsigned long long *part = class_tot + k;                    // 8 (7 used)
+    int32_t *s_beyond = reinterpret_cast<int32_t *>(part + 8);   // 1 (+ padding to 16 bytes)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_beyond + 4);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+
+    const uint32_t G = gridDim.x, b = blockIdx.x;
+    const int32_t img_end_all = image_base + int32_t(n_images);
+    auto nominal = [&](uint64_t i) -> uint64_t {
+        return i >= G ? rows : (((rows / G) * i + (rows % G) * i / G) & ~uint64_t(15));
+    };
+    const uint64_t nom0 = nominal(b), nom1 = nominal(b + 1);
+    auto boundary = [&](uint64_t nom) -> int32_t {
+        const int32_t v = __ldg(image_idx + nom);
+        return v < image_base ? image_base : (v >= img_end_all - 1 ? img_end_all : v + 1);
+    };
+    int32_t I0, I1;
+    if (rows == 0) {
+        I0 = image_base + int32_t(uint64_t(n_images) * b / G);
+        I1 = image_base + int32_t(uint64_t(n_images) * (b + 1) / G);
+    } else {
+        I0 = b == 0 ? image_base : boundary(nom0);
+        I1 = b + 1 == G ? img_end_all : boundary(nom1);
+        if (I1 < I0) I1 = I0;                                     // unsorted input: own nothing
+    }
+    const bool owns = I1 > I0;
+
+    for (uint32_t e = tid; e < T * k; e += kSlabThreads) tile[e] = 0;
+    for (uint32_t c = tid; c < k + 8; c += kSlabThreads) class_tot[c] = 0;      // class totals + partials
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kSlabStages; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // Write images [a, e) (complete, all mine) to d_counts, fold them into the partials, leave their
+    // slots zeroed.  The first min(e - a, T) come from the ring, the rest have no rows.  Uniform.
+    auto flush = [&](int32_t a, int32_t e) {
+        __syncthreads();
+        const uint32_t total = uint32_t(e - a);
+        const uint32_t n_ring = total < T ? total : T;
+        unsigned long long tot[KC], s2 = 0, r = 0, pairs = 0;
+        uint32_t rated = 0, pair_images = 0;
+#pragma unroll
+        for (int cc = 0; cc < KC; ++cc) tot[cc] = 0;
+        for (uint32_t i = wid; i < n_ring; i += kSlabWarps) {
+            const int32_t img = a + int32_t(i);
+            int32_t *src = tile + (uint32_t(img) & tmask) * k;
+            int32_t *dst = counts + size_t(img - image_base) * k;
+            uint32_t n = 0;
+#pragma unroll
+            for (int cc = 0; cc < KC; ++cc) {
+                const uint32_t c = lane + 32u * cc;
+                if (c < k) {
+                    const uint32_t v = uint32_t(src[c]);
+                    dst[c] = int32_t(v);
+                    src[c] = 0;
+                    tot[cc] += v;
+                    s2 += (unsigned long long)v * v;
+                    n += v;
+                }
+            }
+            n = __reduce_add_sync(0xffffffffu, n);
+            r += n;
+            rated += n >= 1;
+            pair_images += n >= 2;
+            pairs += (unsigned long long)n * (n - (n > 0));
+        }
+        if (total > n_ring) {                                     // images without rows
+            int32_t *z = counts + size_t(a - image_base + int32_t(n_ring)) * k;
+            const size_t ne = size_t(total - n_ring) * k;
+            for (size_t i = tid; i < ne; i += kSlabThreads) z[i] = 0;
+        }
+#pragma unroll
+        for (int cc = 0; cc < KC; ++cc)
+            if (lane + 32u * cc < k && tot[cc]) atomicAdd(&class_tot[lane + 32u * cc], tot[cc]);
+        s2 = warp_sum(s2);
+        if (lane == 0) {                                          // r, rated, ... are warp-uniform
+            if (s2) atomicAdd(&part[P_S2], s2);
+            if (r) atomicAdd(&part[P_R], r);
+            if (rated) atomicAdd(&part[P_RATED], (unsigned long long)rated);
+            if (pair_images) atomicAdd(&part[P_PAIR_IMAGES], (unsigned long long)pair_images);
+            if (pairs) atomicAdd(&part[P_PAIRS], pairs);
+        }
+        __syncthreads();
+    };
+
+    uint32_t seen = 0, unsorted = 0;
+    int32_t tb = I0;                                              // first image of the window [tb, tb + T)
+
+    if (rows > 0 && nom0 < rows) {
+        const uint64_t n_stage = (rows - nom0 + kSlabStageRows - 1) / kSlabStageRows;   // upper bound
+        auto stage_idx = [&](int s) { return reinterpret_cast<int32_t *>(ring + size_t(s) * kSlabStageBytes); };
+        // fill ring slot st % kSlabStages with rows [nom0 + st*4224, +4224); all threads call (uniform)
+        auto issue = [&](uint64_t st) {
+            const uint64_t r0 = nom0 + st * kSlabStageRows;
+            const int s = int(st % kSlabStages);
+            int32_t *d_idx = stage_idx(s);
+            uint8_t *d_cls = reinterpret_cast<uint8_t *>(d_idx + kSlabStageRows), *d_act = d_cls + kSlabStageRows;
+            const uint64_t left = rows - r0;
+            uint32_t bulk_rows = kSlabStageRows;
+            if (left < uint64_t(kSlabStageRows)) {                // ragged end of the table
+                bulk_rows = uint32_t(left) & ~15u;
+                for (uint32_t i = bulk_rows + tid; i < uint32_t(kSlabStageRows); i += kSlabThreads) {
+                    const bool in = i < left;
+                    d_idx[i] = in ? image_idx[r0 + i] : INT32_MAX;                // sorts last, owned by nobody
+                    d_cls[i] = in ? class_idx[r0 + i] : uint8_t(0);
+                    d_act[i] = in ? active[r0 + i] : uint8_t(0);
+                }
+            }
+            if (tid == 0) {
+                fence_proxy_async();
+                if (bulk_rows) {
+                    mbar_arrive_expect_tx(&bars[s], bulk_rows * 6u);
+                    bulk_g2s(d_idx, image_idx + r0, bulk_rows * 4u, &bars[s]);
+                    bulk_g2s(d_cls, class_idx + r0, bulk_rows, &bars[s]);
+                    bulk_g2s(d_act, active + r0, bulk_rows, &bars[s]);
+                } else {
+                    mbar_arrive(&bars[s]);
+                }
+            }
+        };
+
+        int32_t prev_last = nom0 > 0 ? __ldg(image_idx + nom0 - 1) : INT32_MIN;         // row before the stage
+        const uint32_t q0 = (uint32_t(kSlabQuads) * wid) / kSlabWarps, q1 = (uint32_t(kSlabQuads) * (wid + 1)) / kSlabWarps;
+        const uint32_t Q0 = lane * kSlabQuads + q0;               // my first quad of a stage
+        uint64_t issued = 0, st = 0;
+        for (; issued < uint64_t(kSlabStages - 1) && issued < n_stage; ++issued) issue(issued);
+        __syncthreads();                                          // ragged-stage plain stores of the prologue
+        for (; st < n_stage; ++st) {
+            if (issued < n_stage) { issue(issued); ++issued; }    // its slot was released by the sync below
+            const int s = int(st % kSlabStages);
+            mbar_wait(&bars[s], uint32_t((st / kSlabStages) & 1));
+            const uint64_t r0 = nom0 + st * kSlabStageRows;
+            const uint32_t valid = rows - r0 < uint64_t(kSlabStageRows) ? uint32_t(rows - r0) : uint32_t(kSlabStageRows);
+            const int32_t *s_idx = stage_idx(s);
+            const int4 *s_quad = reinterpret_cast<const int4 *>(s_idx) + Q0;
+            const uint32_t *s_cls = reinterpret_cast<const uint32_t *>(s_idx + kSlabStageRows) + Q0;
+            const uint32_t *s_act = s_cls + kSlabStageRows / 4;
+            const int32_t first = s_idx[0], last = s_idx[valid - 1];
+            // rows of this stage whose pair (r-1, r) this CTA checks: those below nom1 (a multiple of 16)
+            const uint32_t chk_rows = r0 >= nom1 ? 0u : (nom1 - r0 < uint64_t(kSlabStageRows) ? uint32_t(nom1 - r0) : uint32_t(kSlabStageRows));
+
+            // one pass over my quads for the window [tb, tb + span)
+            auto scan = [&](uint32_t span, bool check_order, bool want_beyond) {
+                const int32_t te = tb + int32_t(span);
+                int32_t prev = Q0 == 0 ? prev_last : s_idx[4 * Q0 - 1];
+                int32_t beyond = INT32_MAX;
+                const uint32_t k4 = 4u * k, tile_s = smem_u32(tile);
+                // my quads [0, n_chk) are order-checked in this pass
+                const uint32_t n_chk = !check_order || chk_rows / 4 <= Q0 ? 0u : chk_rows / 4 - Q0;
+                const uint32_t one = k < 1u ? k : 1u;            // = 1 (k >= 1), but not a literal for ptxas
+                auto quad = [&](uint32_t q) {
+                    const int4 iq = s_quad[q];
+                    const uint32_t cw = s_cls[q], aw = s_act[q];
+                    // quads holding an out-of-order pair (only zero / non-zero matters to the caller)
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.lt.s32 p, %1, %2;\n\t"
+                        "setp.lt.or.s32 p, %3, %1, p;\n\t"
+                        "setp.lt.or.s32 p, %4, %3, p;\n\t"
+                        "setp.lt.or.s32 p, %5, %4, p;\n\t"
+                        "setp.lt.and.u32 p, %6, %7, p;\n\t"
+                        "@p add.u32 %0, %0, 1;\n\t}"
+                        : "+r"(unsorted)
+                        : "r"(iq.x), "r"(prev), "r"(iq.y), "r"(iq.z), "r"(iq.w), "r"(q), "r"(n_chk));
+                    prev = iq.w;
+                    slab_row<0>(iq.x, cw, aw, tb, span, k, tmask, k4, tile_s, one, seen);
+                    slab_row<1>(iq.y, cw, aw, tb, span, k, tmask, k4, tile_s, one, seen);
+                    slab_row<2>(iq.z, cw, aw, tb, span, k, tmask, k4, tile_s, one, seen);
+                    slab_row<3>(iq.w, cw, aw, tb, span, k, tmask, k4, tile_s, one, seen);
+                    if (want_beyond && iq.w >= te) {              // lower bound of the first image past the window
+                        const int32_t cand = iq.x > te ? iq.x : te;
+                        beyond = cand < beyond ? cand : beyond;
+                    }
+                };
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) quad(q);
+                if (q1 - q0 > 4) quad(4);                         // 33 = 8 * 4 + 1: the last warp takes the odd quad
+                if (want_beyond) {
+                    beyond = __reduce_min_sync(0xffffffffu, beyond);
+                    if (lane == 0) atomicMin(s_beyond, beyond);
+                }
+            };
+
+            if (!owns) {
+                scan(0u, true, false);                            // order check only
+            } else {
+                const int32_t lo = first < tb ? tb : (first > I1 ? I1 : first);         // images below are complete
+                const int32_t last_c = last < I1 ? last : I1 - 1;
+                bool more = int64_t(last_c) - int64_t(tb) >= int64_t(T);                // stage does not fit the window
+                if (more && lo > tb) {
+                    flush(tb, lo);
+                    tb = lo;
+                    more = int64_t(last_c) - int64_t(tb) >= int64_t(T);
+                }
+                bool first_pass = true;
+                for (;;) {
+                    const uint32_t span = uint32_t(I1 - tb) < T ? uint32_t(I1 - tb) : T;
+                    if (more) {
+                        if (tid == 0) *s_beyond = INT32_MAX;
+                        __syncthreads();
+                    }
+                    scan(span, first_pass, more);
+                    first_pass = false;
+                    if (!more) break;
+                    __syncthreads();
+                    int32_t nb = *s_beyond;                       // first image with rows past the window (lower bound)
+                    const int32_t te = tb + int32_t(span);
+                    nb = nb < te ? te : (nb > I1 ? I1 : nb);
+                    flush(tb, nb);                                // the window is complete; [te, nb) has no rows
+                    tb = nb;
+                    more = int64_t(last_c) - int64_t(tb) >= int64_t(T);
+                }
+            }
+            prev_last = last;
+            __syncthreads();                                      // everybody is done with ring slot s
+            // past the nominal end and the stream has left my images (or the table ended)
+            if (r0 + kSlabStageRows >= nom1 && (!owns || last >= I1 || r0 + valid >= rows)) { ++st; break; }
+        }
+        // stages issued but not consumed: their copies must land before the shared memory is released
+        for (; st < issued; ++st) mbar_wait(&bars[st % kSlabStages], uint32_t((st / kSlabStages) & 1));
+    }
+    if (tb < I1) flush(tb, I1);                                   // the open window and any trailing images without rows
+    part_add(part, P_ROWS_SEEN, seen);
+    part_add(part, P_UNSORTED, unsorted);
+    __syncthreads();
+    commit_partials(part, class_tot, k, g_partials);
+}
+
 // Any row order: one RED.ADD per active row into a zeroed count matrix.
 __global__ void __launch_bounds__(256)
 tally_scatter_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
@@ -926,7 +1233,8 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
 
 }  // namespace b2
 
-// B2_TALLY_PATH: unset = auto, 0 = thread-per-image kernel, 1 = MATCH.ANY warp kernel, 2 = shared-atomic tile kernel.
+// B2_TALLY_PATH: unset = auto (slab kernel; warp kernel for >= 512 rows per image), 0 = thread-per-image kernel,
+// 1 = MATCH.ANY warp kernel, 2 = shared-atomic tile kernel, 3 = thread-per-row slab kernel.
 static int tally_path_override() {
     const char *e = getenv("B2_TALLY_PATH");
     return e ? atoi(e) : -1;
@@ -963,10 +1271,11 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
     const uint32_t tile_images = pick_tile_images(k);
     const size_t smem = tally_smem_bytes(tile_images, k);
     if (flags & B2_TALLY_SORTED) {
-        // Auto: a thread per image needs many images per buffer phase, so images with very many rows go to the
-        // warp kernel (whose common case is "32 rows of the same image"); everything else to the image kernel.
+        // Auto: the slab kernel keeps the lanes of a warp in different images as long as an image has fewer rows
+        // than a slab; images with very many rows go to the warp kernel (whose common case is "32 rows of the
+        // same image").  The other two kernels stay selectable for comparison (profiles/r1_tally_history.md).
         int path = tally_path_override();
-        if (path < 0) path = (rows / n_images >= 512) ? 1 : 0;
+        if (path < 0) path = (rows / n_images >= 512) ? 1 : 3;
         if (path == 0) {                                     // thread-per-image kernel
             const uint32_t pitch = k | 1u;
             uint32_t ti = 192, cap = 20480;                 // 39 KB counters (k = 50) + 20 KB rows: three CTAs per SM
@@ -993,6 +1302,29 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
                                                                              d_counts, partials);
             B2_LAUNCH_CHECK("tally_image_kernel");
             return B2_OK;
+        }
+        if (path == 3) {                                     // thread-per-row slab kernel
+            uint32_t t = 0;
+            const size_t budget = 110u * 1024u;              // two CTAs per SM
+            while (t < 13 && slab_smem_bytes(2u << t, k) <= budget) ++t;
+            if (const char *e = getenv("B2_TALLY_TILE_LOG2")) t = uint32_t(atoi(e));
+            const size_t smem_slab = slab_smem_bytes(1u << t, k);
+            uint64_t want = rows ? (rows + 2ull * kSlabStageRows - 1) / (2ull * kSlabStageRows)
+                                 : (uint64_t(n_images) + 1023) / 1024;
+            const uint64_t cap_ctas = 2ull * uint64_t(sm_count());
+            if (want > cap_ctas) want = cap_ctas;
+            if (want < 1) want = 1;
+            auto launch = [&](auto kern) -> int {
+                B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(kern), smem_slab));
+                kern<<<uint32_t(want), kSlabThreads, smem_slab, st>>>(d_image_idx, d_class_idx, d_active, rows,
+                                                                     int32_t(image_base), n_images, k, t, d_counts, partials);
+                B2_LAUNCH_CHECK("tally_slab_kernel");
+                return B2_OK;
+            };
+            if (k <= 32) return launch(tally_slab_kernel<1>);
+            if (k <= 64) return launch(tally_slab_kernel<2>);
+            if (k <= 128) return launch(tally_slab_kernel<4>);
+            return launch(tally_slab_kernel<8>);
         }
         if (path == 2) {                                     // shared-memory-atomic tile kernel (comparison only)
             B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_sorted_kernel), smem));

@@ -25,11 +25,13 @@ def _compare(img, cls, act, n_images, k, sorted_by_image, image_base=0):
 
 @pytest.mark.parametrize("n_images,k,n_raters", [(1000, 50, 10), (1, 1, 1), (37, 3, 5), (5000, 50, 100),
                                                  (300, 255, 7), (100_000, 50, 20), (2049, 17, 33), (40, 50, 3000)])
-@pytest.mark.parametrize("mode", ["sorted", "sorted-image-kernel", "sorted-warp-kernel", "sorted-tile-kernel", "scatter"])
+@pytest.mark.parametrize("mode", ["sorted", "sorted-image-kernel", "sorted-warp-kernel", "sorted-tile-kernel",
+                                  "sorted-slab-kernel", "scatter"])
 def test_synthetic_rows(n_images, k, n_raters, mode, monkeypatch):
     """Every sorted-mode kernel (auto choice, thread-per-image, MATCH.ANY warp, shared-atomic tile) and the
     any-order kernel against the oracle, bit-exact."""
-    path = {"sorted-image-kernel": "0", "sorted-warp-kernel": "1", "sorted-tile-kernel": "2"}.get(mode)
+    path = {"sorted-image-kernel": "0", "sorted-warp-kernel": "1", "sorted-tile-kernel": "2",
+            "sorted-slab-kernel": "3"}.get(mode)
     if path is not None:
         monkeypatch.setenv("B2_TALLY_PATH", path)
     img, cls, act = synth_label_rows(n_images, k, n_raters, shuffled=(mode == "scatter"))
@@ -37,6 +39,13 @@ def test_synthetic_rows(n_images, k, n_raters, mode, monkeypatch):
     if n_raters > 1 and p["R"] > 0:
         # constant-n formula on the same integers: bit-identical float64
         assert res.kappa(n_images, n_raters) == fleiss_kappa(p["class_totals"], p["S2"], p["R"], n_images, n_raters)
+
+
+@pytest.fixture(params=["auto", "image", "warp", "tile", "slab"])
+def tally_path(request, monkeypatch):
+    if request.param != "auto":
+        monkeypatch.setenv("B2_TALLY_PATH", {"image": "0", "warp": "1", "tile": "2", "slab": "3"}[request.param])
+    return request.param
 
 
 def test_config1_rows():
@@ -54,7 +63,7 @@ def test_fleiss_1971_through_device(fleiss71):
     assert round(res.kappa(table.shape[0], fleiss71["n_raters"]), 3) == fleiss71["kappa"]
 
 
-def test_edge_cases_sorted():
+def test_edge_cases_sorted(tally_path):
     # no rows at all
     res, _ = _compare(np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.uint8), 777, 5, True)
     assert res.R == 0 and not res.counts.any()
@@ -78,16 +87,26 @@ def test_edge_cases_sorted():
     # non-zero image_base (a shard of the image range)
     img, cls, act = synth_label_rows(500, 50, 12)
     _compare(img + 1000, cls, act, 500, 50, True, image_base=1000)
+    # sparse: few rated images far apart (gaps much longer than any counter window), 1-3 rows each
+    ids = np.sort(rng.choice(2_000_000, size=20_000, replace=False))
+    img = np.repeat(ids, rng.integers(1, 4, size=ids.size)).astype(np.int32)
+    cls = rng.integers(0, 4, size=img.size).astype(np.uint8)
+    _compare(img, cls, np.ones_like(cls), 2_000_000, 4, True)
+    # dense: one row per image (a stage of rows spans thousands of images), k = 200 (small counter window)
+    img = np.arange(30_000, dtype=np.int32)
+    cls = rng.integers(0, 200, size=img.size).astype(np.uint8)
+    act = (rng.random(img.size) < 0.9).astype(np.uint8)
+    _compare(img, cls, act, 30_000, 200, True)
 
 
-def test_unsorted_rows_are_rejected_in_sorted_mode():
+def test_unsorted_rows_are_rejected_in_sorted_mode(tally_path):
     img, cls, act = synth_label_rows(2000, 10, 8, shuffled=True)
     with pytest.raises(ics_b200.B2Error) as e:
         labels.label_tally(img, cls, act, 2000, 10, sorted_by_image=True)
     assert e.value.code == -3
 
 
-def test_out_of_range_rows_are_rejected():
+def test_out_of_range_rows_are_rejected(tally_path):
     img, cls, act = synth_label_rows(100, 10, 8)
     bad = cls.copy()
     bad[17] = 10
