@@ -65,6 +65,22 @@ __device__ __forceinline__ uint32_t addp(uint32_t a, uint32_t b, uint32_t one) {
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
     return d;
 }
+// Variant 2: only the adds that are two-input anyway go to the FMA pipe (one IMAD replaces one IADD, the
+// instruction count does not grow); three-input sums stay IADD3 on the ALU pipe.
+template <int V>
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b, uint32_t one) {
+    return V == 0 ? a + b : addp<1>(a, b, one);
+}
+template <int V>
+__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c, uint32_t one) {
+    if (V == 1) return addp<1>(addp<1>(a, b, one), c, one);
+    if (V == 2) {
+        uint32_t d;                                   // kept as one IADD3: ptxas must not re-associate it with the IMADs
+        asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+        return d;
+    }
+    return a + b + c;
+}
 
 // One 64-byte block.  w[] holds the 16 big-endian message words and is used as the rolling
 // 16-word window of the message schedule (destroyed).
@@ -75,18 +91,20 @@ __device__ __forceinline__ void sha256_compress_v(Sha256State &s, uint32_t (&w)[
 #pragma unroll
     for (int t = 0; t < 64; ++t) {
         if (t >= 16) {
-            w[t & 15] = addp<V>(addp<V>(w[t & 15], B2_SSIG0(w[(t + 1) & 15]), one),
-                                addp<V>(w[(t + 9) & 15], B2_SSIG1(w[(t + 14) & 15]), one), one);
+            w[t & 15] = add2<V>(add3<V>(w[t & 15], B2_SSIG0(w[(t + 1) & 15]), w[(t + 9) & 15], one),
+                                B2_SSIG1(w[(t + 14) & 15]), one);
         }
         // off the critical path: h + K + W (+ d); on it: Sigma1(e) + Ch(e,f,g)
-        const uint32_t hkw = addp<V>(addp<V>(h, kK[t], one), w[t & 15], one);
-        const uint32_t t1 = addp<V>(addp<V>(B2_BSIG1(e), B2_CH(e, f, g), one), hkw, one);
-        const uint32_t t2 = addp<V>(B2_BSIG0(a), B2_MAJ(a, b, c), one);
-        h = g; g = f; f = e; e = addp<V>(d, t1, one);
-        d = c; c = b; b = a; a = addp<V>(t1, t2, one);
+        const uint32_t hkw = add3<V>(h, kK[t], w[t & 15], one);
+        const uint32_t t1 = add3<V>(B2_BSIG1(e), B2_CH(e, f, g), hkw, one);
+        const uint32_t t2 = add2<V>(B2_BSIG0(a), B2_MAJ(a, b, c), one);
+        h = g; g = f; f = e; e = add2<V>(d, t1, one);
+        d = c; c = b; b = a; a = add2<V>(t1, t2, one);
     }
-    s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d;
-    s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+    s.h[0] = add2<V>(s.h[0], a, one); s.h[1] = add2<V>(s.h[1], b, one);
+    s.h[2] = add2<V>(s.h[2], c, one); s.h[3] = add2<V>(s.h[3], d, one);
+    s.h[4] = add2<V>(s.h[4], e, one); s.h[5] = add2<V>(s.h[5], f, one);
+    s.h[6] = add2<V>(s.h[6], g, one); s.h[7] = add2<V>(s.h[7], h, one);
 }
 __device__ __forceinline__ void sha256_compress(Sha256State &s, uint32_t (&w)[16]) { sha256_compress_v<0>(s, w, 1u); }
 
@@ -369,10 +387,13 @@ extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,
     const uint32_t warps = (n + 31) / 32;
     const int block = warps <= uint32_t(sm_count()) * 16u ? 32 : 128;
     const uint32_t grid = (n + block - 1) / block;
-    if (sha_variant_override() == 0)
+    const int variant = sha_variant_override();
+    if (variant == 0)
         sha256_lanes_kernel<0><<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests, 1u);
-    else
+    else if (variant == 1)
         sha256_lanes_kernel<1><<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests, 1u);
+    else
+        sha256_lanes_kernel<2><<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests, 1u);
     B2_LAUNCH_CHECK("sha256_lanes_kernel");
     return B2_OK;
 }

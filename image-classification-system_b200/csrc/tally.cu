@@ -854,13 +854,12 @@ constexpr int kSlabQuads = 33;                                    // quads per s
 constexpr int kSlabRows = 4 * kSlabQuads;                         // 132
 constexpr int kSlabStageRows = 32 * kSlabRows;                    // 4224 (multiple of 16: TMA alignment)
 constexpr int kSlabStageBytes = kSlabStageRows * 6;               // 25 344
-constexpr int kSlabStages = 3;
 constexpr int kSlabThreads = 256;
 constexpr int kSlabWarps = kSlabThreads / 32;
 
-__host__ __device__ inline size_t slab_smem_bytes(uint32_t tile_images, uint32_t k) {
-    return size_t(kSlabStages) * kSlabStageBytes + ((size_t(tile_images) * k * 4 + 15) & ~size_t(15)) + 1024 +
-           size_t(k) * 8 + 8 * 8 + 16 + kSlabStages * 8;
+__host__ __device__ inline size_t slab_smem_bytes(uint32_t stages, uint32_t tile_images, uint32_t k) {
+    return size_t(stages) * kSlabStageBytes + ((size_t(tile_images) * k * 4 + 15) & ~size_t(15)) + 1024 +
+           size_t(k) * 8 + 8 * 8 + 16 + size_t(stages) * 8;
 }
 
 // One row of a quad, branch-free: in the window and class in range => seen++; also active => one shared
@@ -894,7 +893,7 @@ __device__ __forceinline__ void slab_row(int32_t img, uint32_t cw, uint32_t aw, 
           "r"(k4), "r"(tile_s), "r"(one));
 }
 
-template <int KC>                                                 // KC = ceil(k / 32)
+template <int KC, int NS>                                         // KC = classes per lane (k <= 32 KC), NS = ring depth
 __global__ void __launch_bounds__(kSlabThreads, 2)
 tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
                   const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
@@ -903,7 +902,7 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t T = 1u << tile_log2, tmask = T - 1u;
     uint8_t *ring = smem_raw;
-    int32_t *tile = reinterpret_cast<int32_t *>(smem_raw + size_t(kSlabStages) * kSlabStageBytes);
+    int32_t *tile = reinterpret_cast<int32_t *>(smem_raw + size_t(NS) * kSlabStageBytes);
     unsigned long long *class_tot = reinterpret_cast<unsigned long long *>(
         reinterpret_cast<uint8_t *>(tile) + ((size_t(T) * k * 4 + 15) & ~size_t(15)) + 1024);   // pad: see slab_row
     unsigned long long *part = class_tot + k;                    // 8 (7 used)
@@ -936,59 +935,61 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
     for (uint32_t c = tid; c < k + 8; c += kSlabThreads) class_tot[c] = 0;      // class totals + partials
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kSlabStages; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
+    // Per-lane accumulators of the flushes; reduced across the CTA once, at the end of the kernel.
+    unsigned long long tot[KC], s2 = 0, pairs = 0;                // tot[cc]: class lane + 32 cc
+    uint32_t rated = 0, pair_images = 0;
+#pragma unroll
+    for (int cc = 0; cc < KC; ++cc) tot[cc] = 0;
+    auto fold_image = [&](uint32_t n) {                           // n_i of one image (0 is harmless)
+        rated += n >= 1u;
+        pair_images += n >= 2u;
+        pairs += (unsigned long long)n * (n - 1u);                // 0 * 0xffffffff = 0
+    };
+
     // Write images [a, e) (complete, all mine) to d_counts, fold them into the partials, leave their
     // slots zeroed.  The first min(e - a, T) come from the ring, the rest have no rows.  Uniform.
+    // A warp per image, a lane per class; n_i by REDUX, parked in lane (iteration mod 32) so that what
+    // derives from it is computed for 32 images at once.
     auto flush = [&](int32_t a, int32_t e) {
         __syncthreads();
         const uint32_t total = uint32_t(e - a);
         const uint32_t n_ring = total < T ? total : T;
-        unsigned long long tot[KC], s2 = 0, r = 0, pairs = 0;
-        uint32_t rated = 0, pair_images = 0;
-#pragma unroll
-        for (int cc = 0; cc < KC; ++cc) tot[cc] = 0;
-        for (uint32_t i = wid; i < n_ring; i += kSlabWarps) {
+        uint32_t n_mine = 0, it = 0;
+        for (uint32_t i = wid; i < n_ring; i += kSlabWarps, ++it) {
             const int32_t img = a + int32_t(i);
             int32_t *src = tile + (uint32_t(img) & tmask) * k;
             int32_t *dst = counts + size_t(img - image_base) * k;
-            uint32_t n = 0;
+            uint32_t v[KC], n = 0;
 #pragma unroll
             for (int cc = 0; cc < KC; ++cc) {
                 const uint32_t c = lane + 32u * cc;
-                if (c < k) {
-                    const uint32_t v = uint32_t(src[c]);
-                    dst[c] = int32_t(v);
+                v[cc] = (cc < KC / 2 || c < k) ? uint32_t(src[c]) : 0u;           // the lower half of the lanes' classes always exists
+            }
+#pragma unroll
+            for (int cc = 0; cc < KC; ++cc) {
+                const uint32_t c = lane + 32u * cc;
+                if (cc < KC / 2 || c < k) {
+                    dst[c] = int32_t(v[cc]);
                     src[c] = 0;
-                    tot[cc] += v;
-                    s2 += (unsigned long long)v * v;
-                    n += v;
                 }
+                tot[cc] += v[cc];
+                s2 += (unsigned long long)v[cc] * v[cc];
+                n += v[cc];
             }
             n = __reduce_add_sync(0xffffffffu, n);
-            r += n;
-            rated += n >= 1;
-            pair_images += n >= 2;
-            pairs += (unsigned long long)n * (n - (n > 0));
+            if ((it & 31u) == lane) n_mine = n;
+            if ((it & 31u) == 31u) { fold_image(n_mine); n_mine = 0; }
         }
+        fold_image(n_mine);
         if (total > n_ring) {                                     // images without rows
             int32_t *z = counts + size_t(a - image_base + int32_t(n_ring)) * k;
             const size_t ne = size_t(total - n_ring) * k;
             for (size_t i = tid; i < ne; i += kSlabThreads) z[i] = 0;
-        }
-#pragma unroll
-        for (int cc = 0; cc < KC; ++cc)
-            if (lane + 32u * cc < k && tot[cc]) atomicAdd(&class_tot[lane + 32u * cc], tot[cc]);
-        s2 = warp_sum(s2);
-        if (lane == 0) {                                          // r, rated, ... are warp-uniform
-            if (s2) atomicAdd(&part[P_S2], s2);
-            if (r) atomicAdd(&part[P_R], r);
-            if (rated) atomicAdd(&part[P_RATED], (unsigned long long)rated);
-            if (pair_images) atomicAdd(&part[P_PAIR_IMAGES], (unsigned long long)pair_images);
-            if (pairs) atomicAdd(&part[P_PAIRS], pairs);
         }
         __syncthreads();
     };
@@ -997,12 +998,10 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
     int32_t tb = I0;                                              // first image of the window [tb, tb + T)
 
     if (rows > 0 && nom0 < rows) {
-        const uint64_t n_stage = (rows - nom0 + kSlabStageRows - 1) / kSlabStageRows;   // upper bound
-        auto stage_idx = [&](int s) { return reinterpret_cast<int32_t *>(ring + size_t(s) * kSlabStageBytes); };
-        // fill ring slot st % kSlabStages with rows [nom0 + st*4224, +4224); all threads call (uniform)
-        auto issue = [&](uint64_t st) {
-            const uint64_t r0 = nom0 + st * kSlabStageRows;
-            const int s = int(st % kSlabStages);
+        const uint32_t n_stage = uint32_t((rows - nom0 + kSlabStageRows - 1) / kSlabStageRows);   // upper bound
+        auto stage_idx = [&](uint32_t s) { return reinterpret_cast<int32_t *>(ring + size_t(s) * kSlabStageBytes); };
+        // fill ring slot s with rows [r0, r0 + 4224); all threads call (uniform)
+        auto issue = [&](uint64_t r0, uint32_t s) {
             int32_t *d_idx = stage_idx(s);
             uint8_t *d_cls = reinterpret_cast<uint8_t *>(d_idx + kSlabStageRows), *d_act = d_cls + kSlabStageRows;
             const uint64_t left = rows - r0;
@@ -1015,9 +1014,9 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
                     d_cls[i] = in ? class_idx[r0 + i] : uint8_t(0);
                     d_act[i] = in ? active[r0 + i] : uint8_t(0);
                 }
+                fence_proxy_async();
             }
             if (tid == 0) {
-                fence_proxy_async();
                 if (bulk_rows) {
                     mbar_arrive_expect_tx(&bars[s], bulk_rows * 6u);
                     bulk_g2s(d_idx, image_idx + r0, bulk_rows * 4u, &bars[s]);
@@ -1032,14 +1031,28 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
         int32_t prev_last = nom0 > 0 ? __ldg(image_idx + nom0 - 1) : INT32_MIN;         // row before the stage
         const uint32_t q0 = (uint32_t(kSlabQuads) * wid) / kSlabWarps, q1 = (uint32_t(kSlabQuads) * (wid + 1)) / kSlabWarps;
         const uint32_t Q0 = lane * kSlabQuads + q0;               // my first quad of a stage
-        uint64_t issued = 0, st = 0;
-        for (; issued < uint64_t(kSlabStages - 1) && issued < n_stage; ++issued) issue(issued);
+        const uint32_t k4 = 4u * k, tile_s = smem_u32(tile);
+        const uint32_t one = k < 1u ? k : 1u;                     // = 1 (k >= 1), but not a literal for ptxas
+
+        uint32_t issued = 0, st = 0;                              // stages issued / consumed
+        uint32_t is = 0;                                          // ring slot of the next issue
+        uint64_t ir0 = nom0;                                      // first row of the next issue
+        for (; issued < uint32_t(NS - 1) && issued < n_stage; ++issued) {
+            issue(ir0, is);
+            ir0 += kSlabStageRows;
+            is = is + 1 == uint32_t(NS) ? 0u : is + 1;
+        }
         __syncthreads();                                          // ragged-stage plain stores of the prologue
+        uint32_t s = 0, parity = 0;                               // ring slot / mbarrier phase of stage st
+        uint64_t r0 = nom0;
         for (; st < n_stage; ++st) {
-            if (issued < n_stage) { issue(issued); ++issued; }    // its slot was released by the sync below
-            const int s = int(st % kSlabStages);
-            mbar_wait(&bars[s], uint32_t((st / kSlabStages) & 1));
-            const uint64_t r0 = nom0 + st * kSlabStageRows;
+            if (issued < n_stage) {                               // its slot was released by the sync below
+                issue(ir0, is);
+                ir0 += kSlabStageRows;
+                is = is + 1 == uint32_t(NS) ? 0u : is + 1;
+                ++issued;
+            }
+            mbar_wait(&bars[s], parity);
             const uint32_t valid = rows - r0 < uint64_t(kSlabStageRows) ? uint32_t(rows - r0) : uint32_t(kSlabStageRows);
             const int32_t *s_idx = stage_idx(s);
             const int4 *s_quad = reinterpret_cast<const int4 *>(s_idx) + Q0;
@@ -1054,10 +1067,8 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
                 const int32_t te = tb + int32_t(span);
                 int32_t prev = Q0 == 0 ? prev_last : s_idx[4 * Q0 - 1];
                 int32_t beyond = INT32_MAX;
-                const uint32_t k4 = 4u * k, tile_s = smem_u32(tile);
                 // my quads [0, n_chk) are order-checked in this pass
                 const uint32_t n_chk = !check_order || chk_rows / 4 <= Q0 ? 0u : chk_rows / 4 - Q0;
-                const uint32_t one = k < 1u ? k : 1u;            // = 1 (k >= 1), but not a literal for ptxas
                 auto quad = [&](uint32_t q) {
                     const int4 iq = s_quad[q];
                     const uint32_t cw = s_cls[q], aw = s_act[q];
@@ -1102,34 +1113,57 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
                     tb = lo;
                     more = int64_t(last_c) - int64_t(tb) >= int64_t(T);
                 }
-                bool first_pass = true;
-                for (;;) {
-                    const uint32_t span = uint32_t(I1 - tb) < T ? uint32_t(I1 - tb) : T;
-                    if (more) {
-                        if (tid == 0) *s_beyond = INT32_MAX;
+                if (!more) {                                      // the normal case: one pass, no window change
+                    scan(uint32_t(I1 - tb) < T ? uint32_t(I1 - tb) : T, true, false);
+                } else {
+                    bool first_pass = true;
+                    for (;;) {
+                        const uint32_t span = uint32_t(I1 - tb) < T ? uint32_t(I1 - tb) : T;
+                        if (more) {
+                            if (tid == 0) *s_beyond = INT32_MAX;
+                            __syncthreads();
+                        }
+                        scan(span, first_pass, more);
+                        first_pass = false;
+                        if (!more) break;
                         __syncthreads();
+                        int32_t nb = *s_beyond;                   // first image with rows past the window (lower bound)
+                        const int32_t te = tb + int32_t(span);
+                        nb = nb < te ? te : (nb > I1 ? I1 : nb);
+                        flush(tb, nb);                            // the window is complete; [te, nb) has no rows
+                        tb = nb;
+                        more = int64_t(last_c) - int64_t(tb) >= int64_t(T);
                     }
-                    scan(span, first_pass, more);
-                    first_pass = false;
-                    if (!more) break;
-                    __syncthreads();
-                    int32_t nb = *s_beyond;                       // first image with rows past the window (lower bound)
-                    const int32_t te = tb + int32_t(span);
-                    nb = nb < te ? te : (nb > I1 ? I1 : nb);
-                    flush(tb, nb);                                // the window is complete; [te, nb) has no rows
-                    tb = nb;
-                    more = int64_t(last_c) - int64_t(tb) >= int64_t(T);
                 }
             }
             prev_last = last;
             __syncthreads();                                      // everybody is done with ring slot s
             // past the nominal end and the stream has left my images (or the table ended)
-            if (r0 + kSlabStageRows >= nom1 && (!owns || last >= I1 || r0 + valid >= rows)) { ++st; break; }
+            const bool done = r0 + kSlabStageRows >= nom1 && (!owns || last >= I1 || r0 + valid >= rows);
+            r0 += kSlabStageRows;
+            if (++s == uint32_t(NS)) { s = 0; parity ^= 1u; }
+            if (done) { ++st; break; }
         }
         // stages issued but not consumed: their copies must land before the shared memory is released
-        for (; st < issued; ++st) mbar_wait(&bars[st % kSlabStages], uint32_t((st / kSlabStages) & 1));
+        for (; st < issued; ++st) {
+            mbar_wait(&bars[s], parity);
+            if (++s == uint32_t(NS)) { s = 0; parity ^= 1u; }
+        }
     }
     if (tb < I1) flush(tb, I1);                                   // the open window and any trailing images without rows
+
+    // ---- commit: lanes -> CTA (shared, 64-bit) -> global (one atomic per value and CTA) ----
+#pragma unroll
+    for (int cc = 0; cc < KC; ++cc)
+        if (lane + 32u * cc < k && tot[cc]) atomicAdd(&class_tot[lane + 32u * cc], tot[cc]);
+    unsigned long long r = 0;
+#pragma unroll
+    for (int cc = 0; cc < KC; ++cc) r += tot[cc];
+    part_add(part, P_S2, s2);
+    part_add(part, P_R, r);
+    part_add(part, P_RATED, rated);
+    part_add(part, P_PAIR_IMAGES, pair_images);
+    part_add(part, P_PAIRS, pairs);
     part_add(part, P_ROWS_SEEN, seen);
     part_add(part, P_UNSORTED, unsorted);
     __syncthreads();
@@ -1304,14 +1338,17 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
             return B2_OK;
         }
         if (path == 3) {                                     // thread-per-row slab kernel
+            uint32_t stages = 3, per_sm = 2;
+            if (const char *e = getenv("B2_TALLY_STAGES")) stages = atoi(e) == 2 ? 2u : 3u;
+            if (const char *e = getenv("B2_TALLY_CTAS")) per_sm = uint32_t(atoi(e)) < 1 ? 1u : uint32_t(atoi(e));
+            const size_t budget = (227u * 1024u) / per_sm - 1024u;               // per CTA, incl. the 1 KB the driver reserves
             uint32_t t = 0;
-            const size_t budget = 110u * 1024u;              // two CTAs per SM
-            while (t < 13 && slab_smem_bytes(2u << t, k) <= budget) ++t;
+            while (t < 13 && slab_smem_bytes(stages, 2u << t, k) <= budget) ++t;
             if (const char *e = getenv("B2_TALLY_TILE_LOG2")) t = uint32_t(atoi(e));
-            const size_t smem_slab = slab_smem_bytes(1u << t, k);
+            const size_t smem_slab = slab_smem_bytes(stages, 1u << t, k);
             uint64_t want = rows ? (rows + 2ull * kSlabStageRows - 1) / (2ull * kSlabStageRows)
                                  : (uint64_t(n_images) + 1023) / 1024;
-            const uint64_t cap_ctas = 2ull * uint64_t(sm_count());
+            const uint64_t cap_ctas = uint64_t(per_sm) * uint64_t(sm_count());
             if (want > cap_ctas) want = cap_ctas;
             if (want < 1) want = 1;
             auto launch = [&](auto kern) -> int {
@@ -1321,10 +1358,16 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
                 B2_LAUNCH_CHECK("tally_slab_kernel");
                 return B2_OK;
             };
-            if (k <= 32) return launch(tally_slab_kernel<1>);
-            if (k <= 64) return launch(tally_slab_kernel<2>);
-            if (k <= 128) return launch(tally_slab_kernel<4>);
-            return launch(tally_slab_kernel<8>);
+            if (stages == 2) {
+                if (k <= 32) return launch(tally_slab_kernel<1, 2>);
+                if (k <= 64) return launch(tally_slab_kernel<2, 2>);
+                if (k <= 128) return launch(tally_slab_kernel<4, 2>);
+                return launch(tally_slab_kernel<8, 2>);
+            }
+            if (k <= 32) return launch(tally_slab_kernel<1, 3>);
+            if (k <= 64) return launch(tally_slab_kernel<2, 3>);
+            if (k <= 128) return launch(tally_slab_kernel<4, 3>);
+            return launch(tally_slab_kernel<8, 3>);
         }
         if (path == 2) {                                     // shared-memory-atomic tile kernel (comparison only)
             B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_sorted_kernel), smem));

@@ -22,15 +22,18 @@ import ics_b200  # noqa: E402,F401
 from ics_b200 import engine  # noqa: E402
 
 
-def timed(fn):
+def timed(fn, reps=1):
+    """Mean time of `reps` back-to-back launches (after one warm-up).  Short kernels need reps > 1: a single
+    launch between two events also measures the host's launch latency."""
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    fn()
+    for _ in range(reps):
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1)
+    return e0.elapsed_time(e1) / reps
 
 
 def main():
@@ -72,7 +75,8 @@ def main():
         act = (torch.rand(rows, device=dev, generator=g) < 0.95).to(torch.uint8)
         counts = torch.empty((N, k), dtype=torch.int32, device=dev)
         part = torch.empty(k + 7, dtype=torch.int64, device=dev)
-        ms = timed(lambda: engine.label_tally_device(img, cls, act, N, k, 0, True, counts, part))
+        ms = timed(lambda: engine.label_tally_device(img, cls, act, N, k, 0, True, counts, part),
+                   reps=int(os.environ.get("B2_PROF_REPS", "20")))
         b = 6 * rows + 4 * N * k
         print(f"tally: {rows} rows  {ms:.3f} ms  {b / ms / 1e6:.1f} GB/s")
 
