@@ -20,6 +20,8 @@
 //                           compresses from its own padded shared-memory row.
 #include "common.cuh"
 
+#include <mutex>
+
 namespace b2 {
 
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
@@ -387,6 +389,15 @@ extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,
     const uint32_t warps = (n + 31) / 32;
     const int block = warps <= uint32_t(sm_count()) * 16u ? 32 : 128;
     const uint32_t grid = (n + block - 1) / block;
+    // Ask for the shared-memory-heavy L1 split, like the resize kernel: an SM only changes its carve-out
+    // when it is idle, so kernels with different preferences never share an SM and a hash launched beside
+    // a resize on another stream would simply wait for it (measured: no overlap at all without this).
+    static std::once_flag carve_once;
+    std::call_once(carve_once, [] {
+        cudaFuncSetAttribute(sha256_lanes_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(sha256_lanes_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(sha256_lanes_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    });
     const int variant = sha_variant_override();
     if (variant == 0)
         sha256_lanes_kernel<0><<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests, 1u);
