@@ -95,6 +95,7 @@ struct b2_resize_plan {
     int tmp_pitch;        // bytes per intermediate row (multiple of 16)
     int threads;
     int ksh_bucket;       // template bucket for horizontal taps (0 = fast path unavailable)
+    int planar;           // 1 = the planar IDP.4A horizontal pass applies (in_w % 16 == 0, stage fits the register carry)
     size_t smem_fixed;    // ring + intermediate (+ slack); the vertical tap tables add band_rows*(2+ksize_v)*4
     size_t smem_max;      // with band_rows = out_h
 };
@@ -135,10 +136,36 @@ __device__ __forceinline__ uint32_t to_u8(int32_t acc) {
     return kClip ? clip8(acc) : uint32_t(acc) >> kPrecisionBits;
 }
 
-template <int KSH, bool kClip = false>
+// De-interleave 16 RGB pixels (48 bytes, 12 words) into 16 R, 16 G and 16 B bytes: two PRMT per output word.
+__device__ __forceinline__ void planarize16(const uint4 (&in)[3], uint4 &r, uint4 &g, uint4 &b) {
+    const uint32_t w[12] = {in[0].x, in[0].y, in[0].z, in[0].w, in[1].x, in[1].y, in[1].z, in[1].w,
+                            in[2].x, in[2].y, in[2].z, in[2].w};
+    uint32_t rr[4], gg[4], bb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                // pixels 4q..4q+3 = bytes 0..11 of (w0, w1, w2)
+        const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+        rr[q] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);     // bytes 0, 3, 6, 9
+        gg[q] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);     // bytes 1, 4, 7, 10
+        bb[q] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);     // bytes 2, 5, 8, 11
+    }
+    r = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+    g = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+    b = make_uint4(bb[0], bb[1], bb[2], bb[3]);
+}
+
+constexpr int kPlanarChunks = 3;                 // 16-pixel chunks a thread de-interleaves per stage (registers)
+
+// kPlanar: the stage is de-interleaved IN PLACE into an R, a G and a B plane (each thread carries up to
+// kPlanarChunks 48-byte chunks through registers across one barrier), and the horizontal taps run as
+// IDP.4A dot products of four plane bytes with four 8-bit coefficient limbs (a 22-bit coefficient = three
+// limbs, recombined with two shift-adds per output; 8-byte aligned windows read with LDS.64): ~80 instructions
+// per thread and input row instead of ~140 (one PRMT + one IMAD per byte-tap), a third of them on the ALU pipe.  Needs in_w % 16 == 0 (rows are whole 48-byte chunks and start
+// 16-byte aligned) and non-negative coefficients (BILINEAR).  Same integers, same result.
+template <int KSH, bool kClip = false, bool kPlanar = false>
 __global__ void __launch_bounds__(256)
 resize_bands_kernel(const ResizeParams p) {
     constexpr int NV = (3 * KSH + 3) / 4;       // byte-aligned window, in 32-bit words
+    constexpr int NW = 2 * ((KSH + 7 + 7) / 8); // planar: 8-byte aligned window of one plane, in 32-bit words (LDS.64)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
 
@@ -166,6 +193,7 @@ resize_bands_kernel(const ResizeParams p) {
         for (int s = 0; s < p.n_stages; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
+
     // vertical taps of this band -> shared memory
     for (int i = tid; i < (oy1 - oy0) * 2; i += blockDim.x) vb_s[i] = p.vbounds[2 * oy0 + i];
     for (int i = tid; i < (oy1 - oy0) * p.ksize_v; i += blockDim.x) vk_s[i] = p.vcoeffs[oy0 * p.ksize_v + i];
@@ -173,14 +201,33 @@ resize_bands_kernel(const ResizeParams p) {
     // horizontal taps of my column -> registers
     const bool col_active = tid < p.out_w;
     int xmin = 0;
-    int32_t kh[KSH];
+    int32_t kh[kPlanar ? 1 : KSH];
+    // planar: coefficient limbs laid out against the 8-byte aligned window that starts at pixel xmin & ~7
+    uint32_t kl[kPlanar ? 3 : 1][kPlanar ? NW : 1];
+    if (col_active) xmin = p.hbounds[2 * tid];
+    if (!kPlanar) {
 #pragma unroll
-    for (int t = 0; t < KSH; ++t) kh[t] = 0;
-    if (col_active) {
-        xmin = p.hbounds[2 * tid];
+        for (int t = 0; t < KSH; ++t) kh[kPlanar ? 0 : t] = 0;
+        if (col_active) {
 #pragma unroll
-        for (int t = 0; t < KSH; ++t)
-            if (t < p.ksize_h) kh[t] = p.hcoeffs[tid * p.ksize_h + t];
+            for (int t = 0; t < KSH; ++t)
+                if (t < p.ksize_h) kh[kPlanar ? 0 : t] = p.hcoeffs[tid * p.ksize_h + t];
+        }
+    } else {
+        const int off = xmin & 7;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            uint32_t l0 = 0, l1 = 0, l2 = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int t = 4 * j + b - off;                     // tap under byte b of window word j
+                const uint32_t k = (col_active && t >= 0 && t < p.ksize_h) ? uint32_t(p.hcoeffs[tid * p.ksize_h + t]) : 0u;
+                l0 |= (k & 0xffu) << (8 * b);
+                l1 |= ((k >> 8) & 0xffu) << (8 * b);
+                l2 |= ((k >> 16) & 0xffu) << (8 * b);
+            }
+            kl[0][kPlanar ? j : 0] = l0; kl[kPlanar ? 1 : 0][kPlanar ? j : 0] = l1; kl[kPlanar ? 2 : 0][kPlanar ? j : 0] = l2;
+        }
     }
     __syncthreads();
 
@@ -273,7 +320,10 @@ resize_bands_kernel(const ResizeParams p) {
         stage_range(s, b0, b1);
         const uint64_t a0 = b0 & ~uint64_t(15);
         if (aligned) {
-            if (tid == 0 && s + p.n_stages - 1 < total_stages) issue(s + p.n_stages - 1, ibuf);
+            if (tid == 0 && s + p.n_stages - 1 < total_stages) {
+                if (kPlanar) fence_proxy_async();   // the slot was last written by ordinary stores (the planes)
+                issue(s + p.n_stages - 1, ibuf);
+            }
             mbar_wait(&full_bar[buf], parity);
             const uint64_t lim = img_bytes & ~uint64_t(15);
             if (b1 > lim) {            // ragged image tail: uniform branch, last stage of last band
@@ -287,7 +337,61 @@ resize_bands_kernel(const ResizeParams p) {
 
         const int ra = r0 + s * p.rows_per_stage;
         const int rb = min(ra + p.rows_per_stage, r1);
-        if (col_active) {
+        if (kPlanar) {
+            // ---- de-interleave the stage in place: chunk i of the stage (16 pixels, 48 bytes) becomes 16 bytes of
+            // each plane at offset 16 i; a plane holds (rb - ra) rows of in_w bytes, rows contiguous.
+            const uint32_t n_chunks = uint32_t(rb - ra) * uint32_t(p.in_w >> 4);
+            const uint32_t plane_bytes = uint32_t(rb - ra) * uint32_t(p.in_w);
+            uint4 ch[kPlanarChunks][3];
+#pragma unroll
+            for (int i = 0; i < kPlanarChunks; ++i) {
+                const uint32_t idx = tid + i * blockDim.x;
+                if (idx < n_chunks) {
+                    const uint4 *src4 = reinterpret_cast<const uint4 *>(sbuf + size_t(idx) * 48);
+                    ch[i][0] = src4[0]; ch[i][1] = src4[1]; ch[i][2] = src4[2];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < kPlanarChunks; ++i) {
+                const uint32_t idx = tid + i * blockDim.x;
+                if (idx < n_chunks) {
+                    uint4 r4, g4, b4;
+                    planarize16(ch[i], r4, g4, b4);
+                    *reinterpret_cast<uint4 *>(sbuf + size_t(idx) * 16) = r4;
+                    *reinterpret_cast<uint4 *>(sbuf + plane_bytes + size_t(idx) * 16) = g4;
+                    *reinterpret_cast<uint4 *>(sbuf + 2 * plane_bytes + size_t(idx) * 16) = b4;
+                }
+            }
+            __syncthreads();
+            if (col_active) {
+                const uint8_t *src = sbuf + (xmin & ~7);
+                for (int r = ra; r < rb; ++r, src += p.in_w) {
+                    uint32_t out[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        uint32_t w[NW];
+#pragma unroll
+                        for (int j = 0; j < NW; j += 2) {
+                            const uint2 q = *reinterpret_cast<const uint2 *>(src + size_t(c) * plane_bytes + 4 * j);
+                            w[j] = q.x; w[j + 1] = q.y;
+                        }
+                        uint32_t s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+                        for (int j = 0; j < NW; ++j) {
+                            s0 = __dp4a(w[j], kl[0][kPlanar ? j : 0], s0);
+                            s1 = __dp4a(w[j], kl[kPlanar ? 1 : 0][kPlanar ? j : 0], s1);
+                            s2 = __dp4a(w[j], kl[kPlanar ? 2 : 0][kPlanar ? j : 0], s2);
+                        }
+                        out[c] = to_u8<kClip>(int32_t(uint32_t(kRound) + s0 + (s1 << 8) + (s2 << 16)));
+                    }
+                    uint8_t *dst = tmp + size_t((r - r0) & tmp_mask) * p.tmp_pitch + 3 * tid;
+                    dst[0] = uint8_t(out[0]);
+                    dst[1] = uint8_t(out[1]);
+                    dst[2] = uint8_t(out[2]);
+                }
+            }
+        } else if (col_active) {
             // byte address (in shared memory) of my first source byte of row ra; rows are `pitch` apart
             uint32_t src = smem_u32(sbuf) + uint32_t(uint64_t(ra) * pitch - a0) + 3u * xmin;
             for (int r = ra; r < rb; ++r, src += uint32_t(pitch)) {
@@ -304,9 +408,9 @@ resize_bands_kernel(const ResizeParams p) {
 #pragma unroll
                 for (int t = 0; t < KSH; ++t) {
                     const int q0 = 3 * t, q1 = 3 * t + 1, q2 = 3 * t + 2;
-                    acc0 += int32_t(__byte_perm(v[q0 >> 2], 0, 0x4440 | (q0 & 3))) * kh[t];
-                    acc1 += int32_t(__byte_perm(v[q1 >> 2], 0, 0x4440 | (q1 & 3))) * kh[t];
-                    acc2 += int32_t(__byte_perm(v[q2 >> 2], 0, 0x4440 | (q2 & 3))) * kh[t];
+                    acc0 += int32_t(__byte_perm(v[q0 >> 2], 0, 0x4440 | (q0 & 3))) * kh[kPlanar ? 0 : t];
+                    acc1 += int32_t(__byte_perm(v[q1 >> 2], 0, 0x4440 | (q1 & 3))) * kh[kPlanar ? 0 : t];
+                    acc2 += int32_t(__byte_perm(v[q2 >> 2], 0, 0x4440 | (q2 & 3))) * kh[kPlanar ? 0 : t];
                 }
                 uint8_t *dst = tmp + size_t((r - r0) & tmp_mask) * p.tmp_pitch + 3 * tid;
                 dst[0] = uint8_t(to_u8<kClip>(acc0));
@@ -372,12 +476,17 @@ static int pick_bucket(int ksize_h) {
 
 template <int KSH>
 static cudaError_t set_smem_attr(size_t bytes) {
-    return cudaFuncSetAttribute(resize_bands_kernel<KSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    cudaError_t e = cudaFuncSetAttribute(resize_bands_kernel<KSH, false, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(resize_bands_kernel<KSH, false, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
 }
 
 template <int KSH>
-static void launch_bands(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st) {
-    resize_bands_kernel<KSH><<<n * uint32_t(p.n_bands), threads, smem, st>>>(p);
+static void launch_bands(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st, bool planar) {
+    if (planar) resize_bands_kernel<KSH, false, true><<<n * uint32_t(p.n_bands), threads, smem, st>>>(p);
+    else resize_bands_kernel<KSH, false, false><<<n * uint32_t(p.n_bands), threads, smem, st>>>(p);
 }
 
 }  // namespace b2
@@ -425,12 +534,20 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
         pl->smem_fixed = size_t(pl->n_stages) * pl->stage_bytes + size_t(ring_rows) * pl->tmp_pitch + 64;
         pl->smem_max = pl->smem_fixed + size_t(out_h) * (2 + pl->v.ksize) * 4;
     };
+    // Planar IDP.4A pass: rows are whole 48-byte chunks starting 16-byte aligned, and a stage must fit the
+    // register carry of the in-place de-interleave (kPlanarChunks chunks per thread).
+    pl->planar = pl->ksh_bucket != 0 && in_w % 16 == 0 && pl->threads * kPlanarChunks * 48 >= pitch;
+    if (const char *e = getenv("B2_RESIZE_PLANAR")) pl->planar = pl->planar && atoi(e) != 0;
     int rps = 32;
+    if (pl->planar && rps > pl->threads * kPlanarChunks * 48 / pitch) rps = pl->threads * kPlanarChunks * 48 / pitch;
     for (; rps > 1; --rps) {
         layout(rps);
         if (pl->smem_max <= 112 * 1024) break;
     }
-    if (const char *e = getenv("B2_RESIZE_RPS")) rps = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : rps;   // tuning experiments
+    if (const char *e = getenv("B2_RESIZE_RPS")) {                                                         // tuning experiments
+        rps = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : rps;
+        if (rps * pitch > pl->threads * kPlanarChunks * 48) pl->planar = 0;
+    }
     layout(rps);
     if (pl->smem_max > 220 * 1024) pl->ksh_bucket = 0;       // does not fit at all: generic kernel
     *plan_out = pl;
@@ -532,13 +649,13 @@ extern "C" int b2_resize_normalize_batch(const b2_resize_plan *pl, const uint8_t
     }
     B2_CUDA_CHECK(e);
     switch (pl->ksh_bucket) {
-        case 3: launch_bands<3>(p, n, pl->threads, smem_launch, st); break;
-        case 5: launch_bands<5>(p, n, pl->threads, smem_launch, st); break;
-        case 9: launch_bands<9>(p, n, pl->threads, smem_launch, st); break;
-        case 13: launch_bands<13>(p, n, pl->threads, smem_launch, st); break;
-        case 17: launch_bands<17>(p, n, pl->threads, smem_launch, st); break;
-        case 25: launch_bands<25>(p, n, pl->threads, smem_launch, st); break;
-        default: launch_bands<33>(p, n, pl->threads, smem_launch, st); break;
+        case 3: launch_bands<3>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
+        case 5: launch_bands<5>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
+        case 9: launch_bands<9>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
+        case 13: launch_bands<13>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
+        case 17: launch_bands<17>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
+        case 25: launch_bands<25>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
+        default: launch_bands<33>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
     }
     B2_LAUNCH_CHECK("resize_bands_kernel");
     return B2_OK;

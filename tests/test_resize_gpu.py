@@ -24,10 +24,25 @@ def _check(imgs, out_h, out_w, mean=(0, 0, 0), inv_std=(1, 1, 1)):
         np.testing.assert_allclose(prev[i], preview_f32(want, mean, inv_std), rtol=F32_RTOL, atol=1e-7)
 
 
-@pytest.fixture(params=["auto", "generic"])
+def _drop_plans():
+    with engine._plans_lock:
+        plans = list(engine._plans.values())
+        engine._plans.clear()
+    for p in plans:
+        p.close()
+
+
+@pytest.fixture(params=["auto", "bands", "generic"])
 def resize_path(request, monkeypatch):
-    monkeypatch.setenv("B2_RESIZE_PATH", {"auto": "0", "generic": "1"}[request.param])
-    return request.param
+    """auto = planar IDP.4A band kernel where it applies; bands = the PRMT + IMAD band kernel everywhere;
+    generic = the thread-per-output-pixel fallback.  Plans are cached per shape and read the switches when
+    they are created, so the cache is emptied around every case."""
+    monkeypatch.setenv("B2_RESIZE_PATH", "1" if request.param == "generic" else "0")
+    if request.param == "bands":
+        monkeypatch.setenv("B2_RESIZE_PLANAR", "0")
+    _drop_plans()
+    yield request.param
+    _drop_plans()
 
 
 def test_committed_pillow_fixtures(pillow_cases, resize_path):
