@@ -363,6 +363,7 @@ resize_bands_kernel(const ResizeParams p) {
                     *reinterpret_cast<uint4 *>(sbuf + 2 * plane_bytes + size_t(idx) * 16) = b4;
                 }
             }
+            fence_proxy_async();           // my plane stores are ordered before the bulk copy that refills this slot later
             __syncthreads();
             if (col_active) {
                 const uint8_t *src = sbuf + (xmin & ~7);

@@ -99,6 +99,38 @@ def test_edge_cases_sorted(tally_path):
     _compare(img, cls, act, 30_000, 200, True)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_all_sorted_kernels(seed, monkeypatch):
+    """Randomised row distributions (empty images, one-row images, very long images, gaps, odd k, non-zero
+    image_base, ragged table ends) through every sorted-mode kernel, twice each: bit-exact and repeatable."""
+    rng = np.random.default_rng(1000 + seed)
+    n_images = int(rng.integers(1, 6000))
+    k = int(rng.choice([1, 2, 7, 31, 32, 33, 50, 64, 65, 128, 129, 200, 256]))
+    kind = seed % 4
+    if kind == 0:
+        per = rng.integers(0, 60, size=n_images)
+    elif kind == 1:
+        per = (rng.random(n_images) < 0.02) * rng.integers(1, 5000, size=n_images)      # few, long images; big gaps
+    elif kind == 2:
+        per = np.ones(n_images, dtype=np.int64)                                        # one row per image
+    else:
+        per = rng.integers(90, 140, size=n_images)                                     # around one slab per image
+    base = int(rng.integers(0, 1 << 20))
+    img = (np.repeat(np.arange(n_images), per) + base).astype(np.int32)
+    cls = rng.integers(0, k, size=img.size).astype(np.uint8)
+    act = (rng.random(img.size) < 0.9).astype(np.uint8)
+    want = label_tally(img.astype(np.int64) - base, cls, act, n_images, k)
+    for path in (None, "0", "1", "2", "3"):
+        if path is None:
+            monkeypatch.delenv("B2_TALLY_PATH", raising=False)
+        else:
+            monkeypatch.setenv("B2_TALLY_PATH", path)
+        for _ in range(2):
+            res = labels.label_tally(img, cls, act, n_images, k, sorted_by_image=True, image_base=base)
+            assert np.array_equal(res.counts, want), (seed, path, n_images, k, kind)
+            assert res.R == int(act.sum())
+
+
 def test_unsorted_rows_are_rejected_in_sorted_mode(tally_path):
     img, cls, act = synth_label_rows(2000, 10, 8, shuffled=True)
     with pytest.raises(ics_b200.B2Error) as e:
