@@ -14,8 +14,8 @@ synthetic input:
   label step   (`labels.value`, rows/s): BASELINE config 4 shape per GPU — 100 M rows, 1 M images,
       k = 50, clustered by image -> count matrix + integer Fleiss partials (+ all-reduce at N > 1).
 
-`e2e` is the same ingest metric through the host-facing pipeline (pinned HOST buffers, H2D and
-D2H inside the timed region).  `roofline` is for the dominant kernel of the ingest step (the
+`e2e` is the same ingest metric through the host-buffer C ABI (`b2_ingest_stream_*`: pinned HOST buffers
+in, host results out; H2D and D2H inside the timed region).  `roofline` is for the dominant kernel of the ingest step (the
 hash); `kernels` lists every kernel's own roofline.  `cpu_baseline` / `--impl reference` time the
 oracle (hashlib + Pillow + NumPy: the reference's own host libraries) on the box's host cores.
 Inputs are larger than L2 (no flush needed): stated in `config`.
@@ -406,11 +406,18 @@ def run_graft(args):
     h_img, h_cls, h_act = (l_img[:e_rows].cpu().pin_memory(), l_cls[:e_rows].cpu().pin_memory(),
                            l_act[:e_rows].cpu().pin_memory())
 
+    from ics_b200 import labels as b2labels
+    n_img_np, n_cls_np, n_act_np = h_img.numpy(), h_cls.numpy(), h_act.numpy()   # views of the pinned buffers
+
     def label_e2e_step():
-        a, b, c = h_img.to(dev, non_blocking=True), h_cls.to(dev, non_blocking=True), h_act.to(dev, non_blocking=True)
-        cts, p = engine.label_tally_device(a, b, c, e_rows // LABEL_RATERS, LABEL_K)
-        b2dist.allreduce_partials(p)
-        return p.cpu()
+        # one C-ABI call with host pointers: stage, tally, read the partials back (b2_label_tally_host)
+        _, p = b2labels.label_tally_host(n_img_np, n_cls_np, n_act_np, e_rows // LABEL_RATERS, LABEL_K,
+                                         want_counts=False, device=local_rank)
+        if world > 1:
+            t = torch.from_numpy(p).to(dev)
+            b2dist.allreduce_partials(t)
+            p = t.cpu().numpy()
+        return p
 
     ms_le2e, _, _ = timed(label_e2e_step, 5, 2)
     label_e2e = e_rows * world * 5 / (ms_le2e / 1e3)

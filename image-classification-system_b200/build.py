@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb2ingest.so")
-SOURCES = ["api.cu", "sha256.cu", "dedupe.cu", "resize.cu", "tally.cu"]
+SOURCES = ["api.cu", "sha256.cu", "dedupe.cu", "resize.cu", "tally.cu", "host.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "b2ingest.h")]
 
 NVCC_FLAGS = [

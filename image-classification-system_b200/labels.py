@@ -76,13 +76,37 @@ def label_tally(image_idx, class_idx, active, n_images: int, k: int, sorted_by_i
             sorted_by_image = bool(np.all(image_idx[1:] >= image_idx[:-1])) if image_idx.size else True
         else:
             sorted_by_image = True
-    d_img, d_cls, d_act = _rows_to_device(image_idx, class_idx, active, device)
-    counts, partials = engine.label_tally_device(d_img, d_cls, d_act, n_images, k, image_base, sorted_by_image)
-    p = partials.cpu().numpy()
-    engine.check_tally(p, k, d_img.numel())
+    if not any(isinstance(a, torch.Tensor) for a in (image_idx, class_idx, active)):
+        # host rows: one native call with host pointers (b2_label_tally_host stages, tallies, reads back, checks)
+        counts, p = label_tally_host(image_idx, class_idx, active, n_images, k, sorted_by_image, image_base, device)
+    else:
+        d_img, d_cls, d_act = _rows_to_device(image_idx, class_idx, active, device)
+        d_counts, partials = engine.label_tally_device(d_img, d_cls, d_act, n_images, k, image_base, sorted_by_image)
+        p = partials.cpu().numpy()
+        engine.check_tally(p, k, d_img.numel())
+        counts = d_counts.cpu().numpy()
     d = engine.partials_dict(p, k)
-    return TallyResult(counts=counts.cpu().numpy(), class_totals=d["class_totals"], S2=d["S2"], R=d["R"],
+    return TallyResult(counts=counts, class_totals=d["class_totals"], S2=d["S2"], R=d["R"],
                        n_rated=d["n_rated"], n_pairs_images=d["n_pairs_images"], pairs=d["pairs"])
+
+
+def label_tally_host(image_idx, class_idx, active, n_images: int, k: int, sorted_by_image: bool = True,
+                     image_base: int = 0, device: Optional[int] = None, want_counts: bool = True):
+    """Rows in host memory (anything ``np.asarray`` accepts) through ``b2_label_tally_host``: host pointers in,
+    ``(counts int32[n_images,k] or None, partials int64[k+7])`` out; raises ``B2Error`` for unsorted rows
+    (sorted mode) or rows out of range.  No tensor library involved."""
+    from ._lib import B2_PARTIALS_EXTRA, B2_TALLY_SORTED, check, lib
+    dev = engine.init(device)
+    img = np.ascontiguousarray(image_idx, dtype=np.int32)
+    cls = np.ascontiguousarray(class_idx, dtype=np.uint8)
+    act = np.ascontiguousarray(active, dtype=np.uint8)
+    assert img.ndim == 1 and cls.shape == img.shape and act.shape == img.shape
+    counts = np.empty((n_images, k), dtype=np.int32) if want_counts else None
+    partials = np.empty(k + B2_PARTIALS_EXTRA, dtype=np.int64)
+    check(lib.b2_label_tally_host(dev, img.ctypes.data, cls.ctypes.data, act.ctypes.data, img.size, image_base,
+                                  n_images, k, B2_TALLY_SORTED if sorted_by_image else 0,
+                                  counts.ctypes.data if counts is not None else None, partials.ctypes.data))
+    return counts, partials
 
 
 def distinct_images_per_annotator(annotator_idx, image_idx, active, n_annotators: int,

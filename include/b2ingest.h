@@ -155,6 +155,43 @@ int b2_distinct_images_per_annotator(const int32_t *d_annotator_idx, const int32
                                      const uint8_t *d_active, uint64_t rows, uint32_t n_annotators,
                                      uint32_t *d_distinct, void *stream);
 
+/* ---- host-buffer entry points: the end-to-end form of the path --------------------------------
+ * What the reference holds when the path starts is bytes in HOST memory: downloaded files
+ * (app/services/webdav_sync.py:441, the 50-image batch loop :273-283) and rows fetched from table
+ * `classificacoes`.  These entry points take host pointers only and own the device side (staging
+ * buffers, streams, events), so a caller needs nothing but an FFI.  Page-locked buffers
+ * (b2_host_alloc, or any pinned allocation) make the copies asynchronous and full speed; pageable
+ * memory works, slower.
+ *
+ * b2_ingest_stream: fixed-shape batches of n <= max_images decoded RGB images (HWC, packed back to
+ * back, in_h*in_w*3 a multiple of 16) -> 32-byte digests, the dedupe decision of b2_dedupe against
+ * the sorted table h_existing_sorted (m digests, may be NULL/0) and its {processed, created, updated}
+ * counts, uint8 HWC thumbnails and (optional) float32 CHW previews, all in host memory.  The batch is
+ * copied in chunks of chunk_images on one stream; each chunk's hash and resize run on their own
+ * streams beside the remaining copies and their results are read back while later chunks arrive.
+ * submit() only enqueues work and returns; the output buffers are complete when wait() returns
+ * (it also reports the bytes copied each way and the kernels launched).  One batch per stream at a
+ * time; two streams used alternately keep two batches in flight.  h_first_index / h_last_index /
+ * h_previews may be NULL. */
+typedef struct b2_ingest_stream b2_ingest_stream;
+int b2_host_alloc(void **p, uint64_t bytes);
+int b2_host_free(void *p);
+int b2_ingest_stream_create(int device, int in_h, int in_w, int out_h, int out_w, uint32_t max_images,
+                            uint32_t chunk_images, int want_preview, b2_ingest_stream **stream_out);
+int b2_ingest_stream_destroy(b2_ingest_stream *s);
+int b2_ingest_stream_submit(b2_ingest_stream *s, const uint8_t *h_images, uint32_t n,
+                            const uint8_t *h_existing_sorted, uint64_t m,
+                            uint8_t *h_digests, uint8_t *h_is_new, int32_t *h_first_index,
+                            int32_t *h_last_index, uint32_t *h_counts /*3*/,
+                            uint8_t *h_thumbs, float *h_previews);
+int b2_ingest_stream_wait(b2_ingest_stream *s, uint64_t *h2d_bytes, uint64_t *d2h_bytes,
+                          uint32_t *kernel_launches);
+/* Label rows in host memory -> h_partials (int64[k + B2_PARTIALS_EXTRA]) and, if not NULL, the count
+ * matrix h_counts (int32[n_images * k]).  Blocking; returns the verdict of b2_label_tally_status. */
+int b2_label_tally_host(int device, const int32_t *h_image_idx, const uint8_t *h_class_idx,
+                        const uint8_t *h_active, uint64_t rows, uint32_t image_base, uint32_t n_images,
+                        uint32_t k, uint32_t flags, int32_t *h_counts, int64_t *h_partials);
+
 #ifdef __cplusplus
 }
 #endif

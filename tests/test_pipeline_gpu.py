@@ -26,7 +26,7 @@ def test_pipeline_matches_oracle(shape, n, chunk):
     base = [synth_image(g, *shape) for g in range(n - n // 5)]
     images = [base[int(s)] for s in src]
     host = _pinned(images)
-    pipe = IngestPipeline(shape[0], shape[1], n, chunk_images=chunk, n_streams=3)
+    pipe = IngestPipeline(shape[0], shape[1], n, chunk_images=chunk)
     for _ in range(2):                                    # a pipeline object is reusable
         res = pipe.run(host)
         hashes = [sha256_hex(im.tobytes()) for im in images]
@@ -39,6 +39,75 @@ def test_pipeline_matches_oracle(shape, n, chunk):
             assert np.array_equal(res.thumbs[i].numpy(), want)
             np.testing.assert_allclose(res.previews[i].numpy(), preview_f32(want), rtol=1e-5, atol=1e-7)
         assert res.h2d_bytes == n * shape[0] * shape[1] * 3
+
+
+def test_existing_table_and_occurrence_indices():
+    """The sorted table of digests already stored decides created/updated exactly as the sequential reference
+    loop does; first/last occurrence indices come back too."""
+    from ics_b200 import engine
+    shape, n = (64, 80), 30
+    src = synth_duplicate_map(n, 20)
+    base = [synth_image(500 + g, *shape) for g in range(20)]
+    images = [base[int(s)] for s in src]
+    hashes = [sha256_hex(im.tobytes()) for im in images]
+    stored = {hashes[1], hashes[7], sha256_hex(b"not in this batch")}
+    table = engine.sort_digests(np.frombuffer(bytes.fromhex("".join(sorted(stored))), dtype=np.uint8).reshape(-1, 32))
+    res = IngestPipeline(*shape, n, chunk_images=4).run(_pinned(images), torch.from_numpy(table))
+    is_new, first, stats = dedupe_batch(hashes, stored)
+    assert [bool(x) for x in res.is_new.numpy()] == is_new
+    assert res.first_index.tolist() == first and res.stats == stats
+    last = [max(j for j in range(n) if hashes[j] == h) for h in hashes]
+    assert res.last_index.tolist() == last
+
+
+def test_native_stream_from_plain_ctypes_and_numpy():
+    """What a maintainer of the reference would write: no tensor library, the C ABI with host
+    pointers only — page-locked memory from b2_host_alloc viewed as NumPy arrays."""
+    import ctypes as C
+    lib = C.CDLL(ics_b200.LIB_PATH)
+    lib.b2_last_error.restype = C.c_char_p
+    shape, n = (96, 112), 9
+    L = shape[0] * shape[1] * 3
+    images = [synth_image(900 + g, *shape) for g in range(n)]
+
+    def pinned(nbytes, dtype):
+        p = C.c_void_p()
+        assert lib.b2_host_alloc(C.byref(p), C.c_uint64(nbytes)) == 0, lib.b2_last_error()
+        return p, np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (nbytes,)).view(dtype)
+
+    p_in, h_in = pinned(n * L, np.uint8)
+    h_in[:] = np.concatenate([im.reshape(-1) for im in images])
+    p_dig, h_dig = pinned(n * 32, np.uint8)
+    p_new, h_new = pinned(n, np.uint8)
+    p_cnt, h_cnt = pinned(16, np.uint32)
+    p_th, h_th = pinned(n * 256 * 256 * 3, np.uint8)
+    st = C.c_void_p()
+    assert lib.b2_ingest_stream_create(0, shape[0], shape[1], 256, 256, n, 4, 0, C.byref(st)) == 0, lib.b2_last_error()
+    assert lib.b2_ingest_stream_submit(st, p_in, n, None, C.c_uint64(0), p_dig, p_new, None, None, p_cnt, p_th, None) == 0, \
+        lib.b2_last_error()
+    assert lib.b2_ingest_stream_submit(st, p_in, n, None, C.c_uint64(0), p_dig, p_new, None, None, p_cnt, p_th, None) == -1  # busy
+    h2d, d2h, launches = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    assert lib.b2_ingest_stream_wait(st, C.byref(h2d), C.byref(d2h), C.byref(launches)) == 0
+    assert h2d.value == n * L and launches.value == 2 * 3 + 2
+    assert [bytes(d).hex() for d in h_dig.reshape(n, 32)] == [sha256_hex(im.tobytes()) for im in images]
+    assert h_new.tolist() == [1] * n and h_cnt[:3].tolist() == [n, n, 0]
+    assert np.array_equal(h_th.reshape(n, 256, 256, 3)[5], thumbnail_u8(images[5], 256, 256))
+    assert lib.b2_ingest_stream_destroy(st) == 0
+    for p in (p_in, p_dig, p_new, p_cnt, p_th):
+        assert lib.b2_host_free(p) == 0
+
+
+def test_label_tally_host_entry_point():
+    from ics_b200 import labels
+    img, cls, act = synth_label_rows(3000, 50, 12)
+    counts, partials = labels.label_tally_host(img, cls, act, 3000, 50)
+    assert np.array_equal(counts, label_tally(img, cls, act, 3000, 50))
+    assert int(partials[50 + 1]) == int(act.sum()) and int(partials[50 + 5]) == img.size
+    _, p2 = labels.label_tally_host(img, cls, act, 3000, 50, want_counts=False)
+    assert np.array_equal(partials, p2)
+    with pytest.raises(ics_b200.B2Error) as e:
+        labels.label_tally_host(img[::-1].copy(), cls, act, 3000, 50)
+    assert e.value.code == -3
 
 
 def test_two_pipelines_in_flight():
