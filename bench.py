@@ -260,7 +260,7 @@ def run_graft(args):
             engine.sha256_device(flat, offsets, lengths, None, digests)
             side.wait_event(fork)
             with torch.cuda.stream(side):
-                plan.run(flat, offsets, thumb=thumbs, preview=previews)
+                plan.run(flat, offsets, thumb=thumbs, preview=previews, beside_hash=True)
         else:
             plan.run(flat, offsets, thumb=thumbs, preview=previews)
             engine.sha256_device(flat, offsets, lengths, None, digests)
@@ -315,6 +315,7 @@ def run_graft(args):
 
     ms_sha = kernel_ms(lambda: engine.sha256_device(flat, offsets, lengths, None, digests))
     ms_resize = kernel_ms(lambda: plan.run(flat, offsets, thumb=thumbs, preview=previews))
+    ms_resize_bh = kernel_ms(lambda: plan.run(flat, offsets, thumb=thumbs, preview=previews, beside_hash=True))
     ms_dedupe = kernel_ms(lambda: engine.dedupe_device(digests))
 
     # parity spot check against the oracle inside the bench (sampled images; not timed)
@@ -333,7 +334,8 @@ def run_graft(args):
         parity = {"sampled_images": len(idx), "ok": bool(ok), "dedupe_counts": counts_h}
 
     # ---------------- end to end: pinned host buffers through the pipeline ----------------
-    e2e_n = min(args.e2e_images, n_img)
+    # page-locked host memory per rank: the batch + two pipelines' result buffers (~8.3 MB per image)
+    e2e_n = min(args.e2e_images if world <= 2 else min(args.e2e_images, 2048), n_img)
     host_images = torch.empty((e2e_n, IMG_BYTES), dtype=torch.uint8, pin_memory=True)
     host_images.copy_(data[:e2e_n])
     torch.cuda.synchronize()
@@ -471,7 +473,11 @@ def run_graft(args):
                                   "frac of HBM peak is reported for reference, the HBM-bound kernels are under `kernels`"),
             "kernels": {
                 "sha256_lanes_kernel": roof(sha_bytes, ms_sha, "sha256_lanes_kernel"),
-                "resize_bands_kernel": roof(resize_bytes, ms_resize, "resize_bands_kernel"),
+                "resize_bands_kernel": roof(resize_bytes, ms_resize, "resize_bands_kernel",
+                                            note="alone: the PRMT + IMAD horizontal pass (default of b2_resize_normalize_batch)"),
+                "resize_bands_kernel<planar>": roof(resize_bytes, ms_resize_bh, "resize_bands_kernel<planar>",
+                                                    note="B2_RESIZE_BESIDE_HASH: the IDP.4A horizontal pass used inside the ingest "
+                                                         "step, where the hash owns the ALU pipe; timed alone here"),
                 "dedupe (insert+resolve)": {"ms_per_launch": ms_dedupe, "digests": n_img},
                 "tally_slab_kernel": roof(tally_bytes, ms_tally, "tally_slab_kernel"),
             },

@@ -21,6 +21,7 @@ B2_ERR_NO_DEVICE = -4
 B2_ERR_WORKSPACE = -5
 
 B2_TALLY_SORTED = 1
+B2_RESIZE_BESIDE_HASH = 1
 B2_PARTIALS_EXTRA = 7
 
 
@@ -61,6 +62,8 @@ SIGNATURES = {
     "b2_resize_plan_taps": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), _vp, _vp, C.c_uint64]),
     "b2_resize_normalize_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp,
                                             C.POINTER(C.c_float), C.POINTER(C.c_float), _vp]),
+    "b2_resize_normalize_batch_ex": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp,
+                                               C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32, _vp]),
     "b2_label_tally_workspace_bytes": (C.c_uint64, [C.c_uint32]),
     "b2_label_tally": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                  _vp, _vp, _vp, C.c_uint64, _vp]),

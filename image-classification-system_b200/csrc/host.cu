@@ -190,8 +190,8 @@ extern "C" int b2_ingest_stream_submit(b2_ingest_stream *s, const uint8_t *h_ima
         cudaStream_t rs = s->resize[c % kResizeStreams];
         B2_CUDA_CHECK(cudaStreamWaitEvent(rs, s->copied[c], 0));
         float *d_prev = h_previews ? s->d_previews + size_t(lo) * out_px : nullptr;
-        rc = b2_resize_normalize_batch(s->plan, s->d_stage, s->d_offsets + lo, nullptr, cnt, s->d_thumbs + size_t(lo) * out_px,
-                                       d_prev, nullptr, nullptr, rs);
+        rc = b2_resize_normalize_batch_ex(s->plan, s->d_stage, s->d_offsets + lo, nullptr, cnt, s->d_thumbs + size_t(lo) * out_px,
+                                          d_prev, nullptr, nullptr, B2_RESIZE_BESIDE_HASH, rs);
         if (rc != B2_OK) return rc;
         s->launches += 2;
         B2_CUDA_CHECK(cudaMemcpyAsync(h_thumbs + size_t(lo) * out_px, s->d_thumbs + size_t(lo) * out_px, size_t(cnt) * out_px,

@@ -96,6 +96,7 @@ struct b2_resize_plan {
     int threads;
     int ksh_bucket;       // template bucket for horizontal taps (0 = fast path unavailable)
     int planar;           // 1 = the planar IDP.4A horizontal pass applies (in_w % 16 == 0, stage fits the register carry)
+    int vparam;           // 1 = the vertical tap table fits the kernel parameters (out_h * (2 + ksize_v) <= kVtabInts)
     size_t smem_fixed;    // ring + intermediate (+ slack); the vertical tap tables add band_rows*(2+ksize_v)*4
     size_t smem_max;      // with band_rows = out_h
 };
@@ -103,6 +104,7 @@ struct b2_resize_plan {
 namespace b2 {
 
 constexpr int kMaxStages = 4;
+constexpr int kVtabInts = 3456;              // 256 output rows x (2 + 11 taps) = 3328 fit; 13.5 KB of the 32 KB parameter space
 
 struct ResizeParams {
     const uint8_t *rgb;
@@ -116,6 +118,9 @@ struct ResizeParams {
     int band_rows, n_bands, max_band_in_rows;
     int rows_per_stage, stage_bytes, n_stages, tmp_pitch, tmp_ring_rows;
     float mean[3], inv_std[3];
+    // kVParam kernels: the vertical taps of every output row, {first, count, k_0 .. k_{ksize_v-1}} per row, travel
+    // in the kernel parameters (constant bank, uniform loads: no shared-memory traffic, no staging at CTA start).
+    int32_t vtab[kVtabInts];
 };
 
 __device__ __forceinline__ uint32_t clip8(int32_t acc) {
@@ -161,9 +166,9 @@ constexpr int kPlanarChunks = 3;                 // 16-pixel chunks a thread de-
 // limbs, recombined with two shift-adds per output; 8-byte aligned windows read with LDS.64): ~80 instructions
 // per thread and input row instead of ~140 (one PRMT + one IMAD per byte-tap), a third of them on the ALU pipe.  Needs in_w % 16 == 0 (rows are whole 48-byte chunks and start
 // 16-byte aligned) and non-negative coefficients (BILINEAR).  Same integers, same result.
-template <int KSH, bool kClip = false, bool kPlanar = false>
+template <int KSH, bool kClip = false, bool kPlanar = false, bool kVParam = false>
 __global__ void __launch_bounds__(256)
-resize_bands_kernel(const ResizeParams p) {
+resize_bands_kernel(const __grid_constant__ ResizeParams p) {
     constexpr int NV = (3 * KSH + 3) / 4;       // byte-aligned window, in 32-bit words
     constexpr int NW = 2 * ((KSH + 7 + 7) / 8); // planar: 8-byte aligned window of one plane, in 32-bit words (LDS.64)
     extern __shared__ __align__(128) uint8_t smem[];
@@ -184,8 +189,11 @@ resize_bands_kernel(const ResizeParams p) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(img_ptr)) & 15) == 0;
 
     uint8_t *ring = smem;                                            // n_stages * stage_bytes
-    uint8_t *tmp = smem + size_t(p.n_stages) * p.stage_bytes;        // tmp_ring_rows * tmp_pitch (rolling)
-    int32_t *vb_s = reinterpret_cast<int32_t *>(tmp + size_t(p.tmp_ring_rows) * p.tmp_pitch);     // band_rows*2
+    // rolling intermediate: tmp_ring_rows rows of one packed RGBX word per output column
+    uint32_t *tmp = reinterpret_cast<uint32_t *>(smem + size_t(p.n_stages) * p.stage_bytes);
+    const int tmp_pitch_w = p.tmp_pitch >> 2;
+    int32_t *vb_s = reinterpret_cast<int32_t *>(smem + size_t(p.n_stages) * p.stage_bytes +
+                                                size_t(p.tmp_ring_rows) * p.tmp_pitch);            // band_rows*2 (!kVParam)
     int32_t *vk_s = vb_s + 2 * p.band_rows;                          // band_rows * ksize_v
     const int tmp_mask = p.tmp_ring_rows - 1;                        // power of two
 
@@ -194,9 +202,11 @@ resize_bands_kernel(const ResizeParams p) {
         fence_mbar_init();
     }
 
-    // vertical taps of this band -> shared memory
-    for (int i = tid; i < (oy1 - oy0) * 2; i += blockDim.x) vb_s[i] = p.vbounds[2 * oy0 + i];
-    for (int i = tid; i < (oy1 - oy0) * p.ksize_v; i += blockDim.x) vk_s[i] = p.vcoeffs[oy0 * p.ksize_v + i];
+    // vertical taps of this band -> shared memory (unless they came with the kernel parameters)
+    if (!kVParam) {
+        for (int i = tid; i < (oy1 - oy0) * 2; i += blockDim.x) vb_s[i] = p.vbounds[2 * oy0 + i];
+        for (int i = tid; i < (oy1 - oy0) * p.ksize_v; i += blockDim.x) vk_s[i] = p.vcoeffs[oy0 * p.ksize_v + i];
+    }
 
     // horizontal taps of my column -> registers
     const bool col_active = tid < p.out_w;
@@ -277,23 +287,25 @@ resize_bands_kernel(const ResizeParams p) {
     // preview is written with fully coalesced 128-byte stores.
     const float mean0 = p.mean[0], mean1 = p.mean[1], mean2 = p.mean[2];
     const float istd0 = p.inv_std[0], istd1 = p.inv_std[1], istd2 = p.inv_std[2];
+    const int vstride = 2 + p.ksize_v;
+    auto v_first = [&](int oy) { return kVParam ? p.vtab[oy * vstride] : vb_s[2 * (oy - oy0)]; };
+    auto v_count = [&](int oy) { return kVParam ? p.vtab[oy * vstride + 1] : vb_s[2 * (oy - oy0) + 1]; };
+    auto v_coeff = [&](int oy, int t) { return kVParam ? p.vtab[oy * vstride + 2 + t] : vk_s[(oy - oy0) * p.ksize_v + t]; };
     auto emit_ready = [&](int rows_done) {
         int e1 = next_oy;
-        while (e1 < oy1 && vb_s[2 * (e1 - oy0)] + vb_s[2 * (e1 - oy0) + 1] <= rows_done) ++e1;
+        while (e1 < oy1 && v_first(e1) + v_count(e1) <= rows_done) ++e1;
         if (col_active) {
             for (int oy = next_oy; oy < e1; ++oy) {
-                const int ly = oy - oy0;
-                const int ymin = vb_s[2 * ly], cnt = vb_s[2 * ly + 1];
-                const int32_t *vk = vk_s + ly * p.ksize_v;
+                const int cnt = v_count(oy);
                 int32_t a0 = kRound, a1 = kRound, a2 = kRound;
-                const uint8_t *col = tmp + 3 * tid;
-                int rr = ymin - r0;
+                const uint32_t *col = tmp + tid;
+                int rr = v_first(oy) - r0;
                 for (int t = 0; t < cnt; ++t, ++rr) {
-                    const uint8_t *px = col + size_t(rr & tmp_mask) * p.tmp_pitch;
-                    const int32_t k = vk[t];
-                    a0 += int32_t(px[0]) * k;
-                    a1 += int32_t(px[1]) * k;
-                    a2 += int32_t(px[2]) * k;
+                    const uint32_t px = col[size_t(rr & tmp_mask) * tmp_pitch_w];     // one RGBX word per tap
+                    const int32_t k = v_coeff(oy, t);                                  // uniform: constant bank or broadcast
+                    a0 += int32_t(px & 0xffu) * k;
+                    a1 += int32_t(__byte_perm(px, 0, 0x4441)) * k;
+                    a2 += int32_t(__byte_perm(px, 0, 0x4442)) * k;
                 }
                 const uint32_t o0 = to_u8<kClip>(a0), o1 = to_u8<kClip>(a1), o2 = to_u8<kClip>(a2);
                 uint8_t *tpx = thumb + size_t(oy) * row_bytes + 3 * tid;
@@ -386,10 +398,7 @@ resize_bands_kernel(const ResizeParams p) {
                         }
                         out[c] = to_u8<kClip>(int32_t(uint32_t(kRound) + s0 + (s1 << 8) + (s2 << 16)));
                     }
-                    uint8_t *dst = tmp + size_t((r - r0) & tmp_mask) * p.tmp_pitch + 3 * tid;
-                    dst[0] = uint8_t(out[0]);
-                    dst[1] = uint8_t(out[1]);
-                    dst[2] = uint8_t(out[2]);
+                    tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] = out[0] | (out[1] << 8) | (out[2] << 16);
                 }
             }
         } else if (col_active) {
@@ -413,10 +422,8 @@ resize_bands_kernel(const ResizeParams p) {
                     acc1 += int32_t(__byte_perm(v[q1 >> 2], 0, 0x4440 | (q1 & 3))) * kh[kPlanar ? 0 : t];
                     acc2 += int32_t(__byte_perm(v[q2 >> 2], 0, 0x4440 | (q2 & 3))) * kh[kPlanar ? 0 : t];
                 }
-                uint8_t *dst = tmp + size_t((r - r0) & tmp_mask) * p.tmp_pitch + 3 * tid;
-                dst[0] = uint8_t(to_u8<kClip>(acc0));
-                dst[1] = uint8_t(to_u8<kClip>(acc1));
-                dst[2] = uint8_t(to_u8<kClip>(acc2));
+                tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] =
+                    to_u8<kClip>(acc0) | (to_u8<kClip>(acc1) << 8) | (to_u8<kClip>(acc2) << 16);
             }
         }
         __syncthreads();               // stage consumed (ring slot reusable), intermediate rows visible
@@ -477,17 +484,25 @@ static int pick_bucket(int ksize_h) {
 
 template <int KSH>
 static cudaError_t set_smem_attr(size_t bytes) {
-    cudaError_t e = cudaFuncSetAttribute(resize_bands_kernel<KSH, false, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(resize_bands_kernel<KSH, false, true>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    const void *fns[4] = {reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, false, false>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, true, false>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, false, true>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, true, true>)};
+    for (const void *fn : fns) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 template <int KSH>
-static void launch_bands(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st, bool planar) {
-    if (planar) resize_bands_kernel<KSH, false, true><<<n * uint32_t(p.n_bands), threads, smem, st>>>(p);
-    else resize_bands_kernel<KSH, false, false><<<n * uint32_t(p.n_bands), threads, smem, st>>>(p);
+static void launch_bands(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st, bool planar,
+                         bool vparam) {
+    const uint32_t grid = n * uint32_t(p.n_bands);
+    if (planar && vparam) resize_bands_kernel<KSH, false, true, true><<<grid, threads, smem, st>>>(p);
+    else if (planar) resize_bands_kernel<KSH, false, true, false><<<grid, threads, smem, st>>>(p);
+    else if (vparam) resize_bands_kernel<KSH, false, false, true><<<grid, threads, smem, st>>>(p);
+    else resize_bands_kernel<KSH, false, false, false><<<grid, threads, smem, st>>>(p);
 }
 
 }  // namespace b2
@@ -517,7 +532,9 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
     pl->threads = ((out_w + 31) / 32) * 32;
     if (pl->threads > 256) pl->ksh_bucket = 0;           // thread-per-column layout: out_w <= 256
     const int pitch = in_w * 3;
-    pl->tmp_pitch = ((out_w * 3 + 15) / 16) * 16;
+    pl->tmp_pitch = ((out_w * 4 + 15) / 16) * 16;
+    pl->vparam = out_h * (2 + pl->v.ksize) <= kVtabInts;
+    if (const char *e = getenv("B2_RESIZE_VPARAM")) pl->vparam = pl->vparam && atoi(e) != 0;
     // Stage geometry.  The per-stage barrier + refill costs ~80 instructions per thread and stalls the CTA,
     // so a stage should hold as many rows as fit while TWO CTAs still share an SM (<= 112 KB each):
     // two stages (the second CTA covers the refill latency), measured best on 1080p at 6 rows per stage
@@ -533,12 +550,13 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
         while (ring_rows < 2 * rps + pl->v.ksize + 2) ring_rows <<= 1;   // two stages plus one tap window
         pl->tmp_ring_rows = ring_rows;
         pl->smem_fixed = size_t(pl->n_stages) * pl->stage_bytes + size_t(ring_rows) * pl->tmp_pitch + 64;
-        pl->smem_max = pl->smem_fixed + size_t(out_h) * (2 + pl->v.ksize) * 4;
+        pl->smem_max = pl->smem_fixed + (pl->vparam ? 0 : size_t(out_h) * (2 + pl->v.ksize) * 4);
     };
     // Planar IDP.4A pass: rows are whole 48-byte chunks starting 16-byte aligned, and a stage must fit the
     // register carry of the in-place de-interleave (kPlanarChunks chunks per thread).
     pl->planar = pl->ksh_bucket != 0 && in_w % 16 == 0 && pl->threads * kPlanarChunks * 48 >= pitch;
-    if (const char *e = getenv("B2_RESIZE_PLANAR")) pl->planar = pl->planar && atoi(e) != 0;
+    // pl->planar says the planar pass is POSSIBLE for this shape; which pass a call uses is decided per call
+    // (B2_RESIZE_BESIDE_HASH flag, or B2_RESIZE_PLANAR=0/1 to force one for tests and comparisons).
     int rps = 32;
     if (pl->planar && rps > pl->threads * kPlanarChunks * 48 / pitch) rps = pl->threads * kPlanarChunks * 48 / pitch;
     for (; rps > 1; --rps) {
@@ -587,6 +605,13 @@ extern "C" int b2_resize_normalize_batch(const b2_resize_plan *pl, const uint8_t
                                          const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,
                                          uint8_t *d_thumb, float *d_preview, const float mean[3],
                                          const float inv_std[3], void *stream) {
+    return b2_resize_normalize_batch_ex(pl, d_rgb, d_offsets, d_out_slot, n, d_thumb, d_preview, mean, inv_std, 0u, stream);
+}
+
+extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint8_t *d_rgb,
+                                            const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,
+                                            uint8_t *d_thumb, float *d_preview, const float mean[3],
+                                            const float inv_std[3], uint32_t flags, void *stream) {
     using namespace b2;
     if (n == 0) return B2_OK;
     B2_REQUIRE(pl && d_rgb && d_offsets && d_thumb, "b2_resize_normalize_batch: null pointer");
@@ -610,11 +635,23 @@ extern "C" int b2_resize_normalize_batch(const b2_resize_plan *pl, const uint8_t
     p.max_band_in_rows = 0;
     p.rows_per_stage = pl->rows_per_stage; p.stage_bytes = pl->stage_bytes; p.n_stages = pl->n_stages;
     p.tmp_pitch = pl->tmp_pitch; p.tmp_ring_rows = pl->tmp_ring_rows;
-    const size_t smem_launch = pl->smem_fixed + size_t(p.band_rows) * (2 + pl->v.ksize) * 4;
+    const size_t smem_launch = pl->smem_fixed + (pl->vparam ? 0 : size_t(p.band_rows) * (2 + pl->v.ksize) * 4);
+    if (pl->vparam) {
+        const int vs = 2 + pl->v.ksize;
+        for (int oy = 0; oy < pl->out_h; ++oy) {
+            p.vtab[oy * vs] = pl->v.bounds[2 * oy];
+            p.vtab[oy * vs + 1] = pl->v.bounds[2 * oy + 1];
+            memcpy(&p.vtab[oy * vs + 2], &pl->v.coeffs[size_t(oy) * pl->v.ksize], size_t(pl->v.ksize) * 4);
+        }
+    }
     for (int c = 0; c < 3; ++c) {
         p.mean[c] = mean ? mean[c] : 0.0f;
         p.inv_std[c] = inv_std ? inv_std[c] : 1.0f;
     }
+    // Horizontal pass: the bands pass (PRMT + IMAD) is the faster one alone; the planar pass (IDP.4A) needs a
+    // third of its ALU work and is the faster one when a hash kernel shares the SMs.
+    bool planar = pl->planar != 0 && (flags & B2_RESIZE_BESIDE_HASH) != 0;
+    if (const char *e = getenv("B2_RESIZE_PLANAR")) planar = pl->planar != 0 && atoi(e) != 0;
     const bool fast = pl->ksh_bucket != 0 && resize_path_override() != 1 &&
                       uint64_t(n) * uint64_t(p.n_bands) < 0x7fffffffull;
     if (!fast) {
@@ -650,13 +687,13 @@ extern "C" int b2_resize_normalize_batch(const b2_resize_plan *pl, const uint8_t
     }
     B2_CUDA_CHECK(e);
     switch (pl->ksh_bucket) {
-        case 3: launch_bands<3>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
-        case 5: launch_bands<5>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
-        case 9: launch_bands<9>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
-        case 13: launch_bands<13>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
-        case 17: launch_bands<17>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
-        case 25: launch_bands<25>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
-        default: launch_bands<33>(p, n, pl->threads, smem_launch, st, pl->planar != 0); break;
+        case 3: launch_bands<3>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
+        case 5: launch_bands<5>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
+        case 9: launch_bands<9>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
+        case 13: launch_bands<13>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
+        case 17: launch_bands<17>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
+        case 25: launch_bands<25>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
+        default: launch_bands<33>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
     }
     B2_LAUNCH_CHECK("resize_bands_kernel");
     return B2_OK;

@@ -392,8 +392,10 @@ extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,
     // Ask for the shared-memory-heavy L1 split, like the resize kernel: an SM only changes its carve-out
     // when it is idle, so kernels with different preferences never share an SM and a hash launched beside
     // a resize on another stream would simply wait for it (measured: no overlap at all without this).
-    static std::once_flag carve_once;
-    std::call_once(carve_once, [] {
+    static std::once_flag carve_once[64];                    // function attributes are per device
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    std::call_once(carve_once[cur_dev & 63], [] {
         cudaFuncSetAttribute(sha256_lanes_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(sha256_lanes_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(sha256_lanes_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

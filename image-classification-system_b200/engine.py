@@ -227,9 +227,10 @@ class ResizePlan:
     def run(self, rgb: torch.Tensor, offsets: torch.Tensor, thumb: Optional[torch.Tensor] = None,
             preview: Optional[torch.Tensor] = None, want_preview: bool = True,
             mean: Sequence[float] = (0.0, 0.0, 0.0), inv_std: Sequence[float] = (1.0, 1.0, 1.0),
-            out_slot: Optional[torch.Tensor] = None):
+            out_slot: Optional[torch.Tensor] = None, beside_hash: bool = False):
         """rgb: uint8 device buffer holding n HWC images at byte ``offsets`` (int64[n]).
-        Returns (thumb uint8[n,out_h,out_w,3], preview float32[n,3,out_h,out_w] or None)."""
+        Returns (thumb uint8[n,out_h,out_w,3], preview float32[n,3,out_h,out_w] or None).
+        ``beside_hash``: a hash kernel runs on another stream at the same time (B2_RESIZE_BESIDE_HASH)."""
         _need_cuda(rgb, offsets, thumb, preview, out_slot)
         init(rgb.device.index)
         n = offsets.numel()
@@ -242,8 +243,9 @@ class ResizePlan:
             preview = torch.empty((n, 3, self.out_h, self.out_w), dtype=torch.float32, device=rgb.device)
         m = (C.c_float * 3)(*[float(x) for x in mean])
         s = (C.c_float * 3)(*[float(x) for x in inv_std])
-        check(lib.b2_resize_normalize_batch(self._h, _ptr(rgb), _ptr(offsets), _ptr(out_slot), n,
-                                            _ptr(thumb), _ptr(preview), m, s, _stream()))
+        check(lib.b2_resize_normalize_batch_ex(self._h, _ptr(rgb), _ptr(offsets), _ptr(out_slot), n,
+                                               _ptr(thumb), _ptr(preview), m, s,
+                                               _lib.B2_RESIZE_BESIDE_HASH if beside_hash else 0, _stream()))
         return thumb, preview
 
 

@@ -108,6 +108,14 @@ int b2_resize_normalize_batch(const b2_resize_plan *plan, const uint8_t *d_rgb,
                               const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,
                               uint8_t *d_thumb, float *d_preview,
                               const float mean[3], const float inv_std[3], void *stream);
+/* Same with flags.  B2_RESIZE_BESIDE_HASH: the caller runs b2_sha256_batch on another stream at the same
+ * time; the kernel then uses the horizontal pass that leaves the INT32 ALU pipe to the hash (identical
+ * results, slower alone, faster together). */
+#define B2_RESIZE_BESIDE_HASH 1u
+int b2_resize_normalize_batch_ex(const b2_resize_plan *plan, const uint8_t *d_rgb,
+                                 const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,
+                                 uint8_t *d_thumb, float *d_preview,
+                                 const float mean[3], const float inv_std[3], uint32_t flags, void *stream);
 
 /* ---- a13: per-image label tally + Fleiss partials ---------------------------------------
  * Absent in the reference (it only groups one user's rows, app/crud/classificacao_crud.py:

@@ -32,14 +32,15 @@ def _drop_plans():
         p.close()
 
 
-@pytest.fixture(params=["auto", "bands", "generic"])
+@pytest.fixture(params=["auto", "planar", "generic"])
 def resize_path(request, monkeypatch):
-    """auto = planar IDP.4A band kernel where it applies; bands = the PRMT + IMAD band kernel everywhere;
-    generic = the thread-per-output-pixel fallback.  Plans are cached per shape and read the switches when
+    """auto = the band kernel with the PRMT + IMAD horizontal pass (what a plain call gets); planar = the band
+    kernel with the IDP.4A pass forced wherever the shape allows it (what B2_RESIZE_BESIDE_HASH selects);
+    generic = the thread-per-output-pixel fallback.  Plans are cached per shape and read some switches when
     they are created, so the cache is emptied around every case."""
     monkeypatch.setenv("B2_RESIZE_PATH", "1" if request.param == "generic" else "0")
-    if request.param == "bands":
-        monkeypatch.setenv("B2_RESIZE_PLANAR", "0")
+    if request.param == "planar":
+        monkeypatch.setenv("B2_RESIZE_PLANAR", "1")
     _drop_plans()
     yield request.param
     _drop_plans()
