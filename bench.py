@@ -403,6 +403,15 @@ def run_graft(args):
                                   LABEL_IMAGES * world, LABEL_RATERS)
     ms_tally = kernel_ms(lambda: engine.label_tally_device(l_img, l_cls, l_act, LABEL_IMAGES, LABEL_K, 0, True,
                                                            l_counts, l_part), reps=20)
+    # the same rows in random order (a heap scan instead of an index scan on id_img): any-order path =
+    # zeroed matrix + global RED.ADD (L2-atomic bound) + partials pass; reported for information
+    perm = torch.randperm(rows, device=dev, generator=gl)
+    s_img, s_cls, s_act = l_img[perm].contiguous(), l_cls[perm].contiguous(), l_act[perm].contiguous()
+    del perm
+    ms_scatter = kernel_ms(lambda: engine.label_tally_device(s_img, s_cls, s_act, LABEL_IMAGES, LABEL_K, 0, False,
+                                                             l_counts, l_part), reps=5)
+    scatter_ok = bool(torch.equal(l_part[:LABEL_K + 5].cpu(), torch.from_numpy(local[:LABEL_K + 5])))
+    del s_img, s_cls, s_act
     # labels e2e: rows in pinned host memory -> device -> tally -> partials back on the host
     e_rows = 20_000_000
     h_img, h_cls, h_act = (l_img[:e_rows].cpu().pin_memory(), l_cls[:e_rows].cpu().pin_memory(),
@@ -487,6 +496,9 @@ def run_graft(args):
             "labels": {"value": rows_per_s, "unit": "rows/s", "rows_per_gpu_per_step": rows, "steps": label_steps,
                        "ms_per_step": ms_labels / label_steps, "gpu_launches": label_launches,
                        "roofline": roof(tally_bytes, ms_tally, "tally_slab_kernel"), "kappa": kappa, "partials_ok": bool(label_ok),
+                       "shuffled_rows": {"value": rows / (ms_scatter / 1e3), "unit": "rows/s per GPU", "ms_per_launch": ms_scatter,
+                                         "path": "memset + tally_scatter_kernel (global RED.ADD) + fleiss_partials_kernel",
+                                         "same_partials_as_sorted": scatter_ok},
                        "e2e": {"value": label_e2e, "unit": "rows/s", "rows_per_step": e_rows,
                                "h2d_bytes_per_step": 6 * e_rows, "d2h_bytes_per_step": 8 * (LABEL_K + 7)}},
             "parity": parity,
