@@ -247,20 +247,28 @@ def run_graft(args):
     previews = torch.empty((n_img, 3, OUT, OUT), dtype=torch.float32, device=dev)
     plan = engine.get_plan(IMG_H, IMG_W, OUT, OUT, local_rank)
     global_index = (torch.arange(n_img, dtype=torch.int32, device=dev) * world + rank)   # image g = i*G + rank
-    side = torch.cuda.Stream(dev)
+    side = torch.cuda.Stream(dev)                            # resize (default = lowest priority)
+    hstream = torch.cuda.Stream(dev, priority=-1)            # hash (higher priority: its CTAs are placed first)
     launches = {"n": 0}
+    per_step = {"ms": []}
 
     def ingest_step():
         main = torch.cuda.current_stream()
         if args.overlap:
             # The hash keeps one warp per SM sub-partition busy on the INT32 ALU pipe for the whole step and
             # leaves HBM and most issue slots idle: the HBM-bound resize runs beside it on a second stream.
+            # The hash stream has the higher priority, so its 592 one-warp CTAs are placed first (four per SM,
+            # one per sub-partition) and the resize CTAs fill in around them.
             fork = torch.cuda.Event()
             fork.record(main)
-            engine.sha256_device(flat, offsets, lengths, None, digests)
+            hstream.wait_event(fork)
             side.wait_event(fork)
+            with torch.cuda.stream(hstream):
+                engine.sha256_device(flat, offsets, lengths, None, digests)
             with torch.cuda.stream(side):
                 plan.run(flat, offsets, thumb=thumbs, preview=previews, beside_hash=True)
+            main.wait_stream(hstream)
+            main.wait_stream(side)
         else:
             plan.run(flat, offsets, thumb=thumbs, preview=previews)
             engine.sha256_device(flat, offsets, lengths, None, digests)
@@ -268,8 +276,6 @@ def run_graft(args):
             is_new, counts = b2dist.global_dedupe(digests, global_index)
         else:
             is_new, _, _, counts = engine.dedupe_device(digests)
-        if args.overlap:
-            main.wait_stream(side)
         launches["n"] += 4
         return is_new, counts
 
@@ -278,15 +284,18 @@ def run_graft(args):
             fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         launches["n"] = 0
         t0 = time.time()
         e0.record()
         out = None
-        for _ in range(steps):
+        for i in range(steps):
             out = fn()
+            marks[i].record()
         e1.record()
         barrier()
         t1 = time.time()
+        per_step["ms"] = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
         return max_over_ranks(e0.elapsed_time(e1)), out, (t0, t1)
 
     sampler = ClockSampler(local_rank)
@@ -296,6 +305,7 @@ def run_graft(args):
 
     ms_ingest, (is_new, counts), window = timed(ingest_step, args.steps, args.warmup)
     ingest_launches = launches["n"]
+    ingest_step_ms = list(per_step["ms"])
     counts_h = counts.cpu().tolist()
     total_images = n_img * world * args.steps
     value = total_images / (ms_ingest / 1e3)
@@ -439,10 +449,10 @@ def run_graft(args):
         resize_bytes = n_img * (IMG_BYTES + THUMB_BYTES + PREVIEW_BYTES)
         tally_bytes = 6 * rows + 4 * LABEL_IMAGES * LABEL_K
 
-        # DRAM traffic per launch: the ratio measured by ncu on the profiling workload (profiles/r1b_traffic.json,
+        # DRAM traffic per launch: the ratio measured by ncu on the profiling workload (profiles/traffic.json,
         # committed with the ncu summary it comes from), scaled to this launch's algorithmic bytes.
         try:
-            with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 ncu = json.load(f)
         except (OSError, ValueError):
             ncu = {}
@@ -455,7 +465,7 @@ def run_graft(args):
             if m:
                 d["traffic"] = bytes_ * m["dram_bytes"] / m["algorithmic_bytes"]
                 d["traffic_source"] = (f"ncu dram bytes / algorithmic bytes = {m['dram_bytes'] / m['algorithmic_bytes']:.4f} "
-                                       f"on {m['workload']} (profiles/r1b_traffic.json), scaled to this launch")
+                                       f"on {m['workload']} (profiles/traffic.json), scaled to this launch")
                 d["pipes_ncu"] = {"alu_pct": m["alu_pipe_pct"], "fma_pct": m["fma_pipe_pct"], "issue_slots_pct": m["issue_slots_pct"]}
             if note:
                 d["note"] = note
@@ -475,7 +485,7 @@ def run_graft(args):
                     "images_per_step": e2e_n, "chunk_images": args.e2e_chunk, "steps": e2e_steps,
                     "gpu_launches_per_step": e2e_launches, "pipelining": "2 batches in flight (submit i+1 before result i)",
                     "matches_device_path": e2e_ok},
-            "gpu_launches": ingest_launches,
+            "gpu_launches": ingest_launches, "step_ms_rank0": ingest_step_ms,
             "roofline": roof(sha_bytes, ms_sha, "sha256_lanes_kernel",
                              note="dominant kernel of the ingest step (79 % of it); sha256 is bound by the INT32 ALU pipe "
                                   "(1 290 ALU instructions per 64-byte block, pipe 90 % busy under ncu), not by HBM: "

@@ -135,10 +135,14 @@ extern "C" int b2_ingest_stream_create(int device, int in_h, int in_w, int out_h
         B2_TRY(cudaMemcpy(s->d_offsets, off.data(), size_t(max_images) * 8, cudaMemcpyHostToDevice));
         B2_TRY(cudaMemcpy(s->d_lengths, len.data(), size_t(max_images) * 8, cudaMemcpyHostToDevice));
     }
-    B2_TRY(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
-    B2_TRY(cudaStreamCreateWithFlags(&s->fin, cudaStreamNonBlocking));
-    for (auto &st : s->hash) B2_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto &st : s->resize) B2_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    // The hash kernels are the long pole (~130 ms each whatever the chunk size) and want one warp per SM
+    // sub-partition: their streams get the higher priority, so their CTAs are placed before the resize CTAs.
+    int prio_low = 0, prio_high = 0;
+    B2_TRY(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+    B2_TRY(cudaStreamCreateWithPriority(&s->copy, cudaStreamNonBlocking, prio_low));
+    B2_TRY(cudaStreamCreateWithPriority(&s->fin, cudaStreamNonBlocking, prio_low));
+    for (auto &st : s->hash) B2_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_high));
+    for (auto &st : s->resize) B2_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_low));
     const uint32_t n_chunks = (max_images + s->chunk - 1) / s->chunk;
     s->copied.assign(n_chunks, nullptr);
     for (auto &e : s->copied) B2_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
