@@ -212,6 +212,10 @@ def run_graft(args):
     dev = torch.device("cuda", local_rank)
     engine.init(local_rank)
     hbm_peak, peak_src = peaks()
+    # host side of the end-to-end runs: page-locked buffers on the NUMA node next to this rank's GPU
+    # (undone before the CPU baseline, which uses every host core)
+    affinity0 = os.sched_getaffinity(0)
+    numa_node = engine.bind_host_thread_to_gpu_node(local_rank)
 
     def barrier():
         if world > 1:
@@ -443,6 +447,7 @@ def run_graft(args):
     ms_le2e, _, _ = timed(label_e2e_step, 5, 2)
     label_e2e = e_rows * world * 5 / (ms_le2e / 1e3)
 
+    os.sched_setaffinity(0, affinity0)
     if rank == 0:
         sampler.stop()
         sha_bytes = n_img * (IMG_BYTES + 32)
@@ -484,6 +489,7 @@ def run_graft(args):
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "images_per_step": e2e_n, "chunk_images": args.e2e_chunk, "steps": e2e_steps,
                     "gpu_launches_per_step": e2e_launches, "pipelining": "2 batches in flight (submit i+1 before result i)",
+                    "host_numa_node_rank0": numa_node,
                     "matches_device_path": e2e_ok},
             "gpu_launches": ingest_launches, "step_ms_rank0": ingest_step_ms,
             "roofline": roof(sha_bytes, ms_sha, "sha256_lanes_kernel",
