@@ -7,27 +7,11 @@
 // table `classificacoes` (app/db/models.py:224-241): image_idx int32 (id_img), class_idx uint8
 // (id_opc), active uint8 (ativo); only rows with active != 0 count (classificacao_crud.py:314).
 //
-// tally_sorted_kernel — rows ordered by image_idx (an index scan on id_img).  HBM-bound:
-//   6 B read per row + 4*k B written per image, every byte touched once.
-//   * Persistent CTAs.  CTA b nominally owns rows [b*R/G, (b+1)*R/G); so that every image is
-//     written by exactly one CTA with plain stores, the boundary is moved to the next image
-//     change: CTA b owns images [I_b, I_{b+1}), I_b = image_idx[b*R/G] + 1.  It starts
-//     streaming at its nominal row and simply ignores rows of foreign images, so no search
-//     and no pre-pass is needed.
-//   * A thread loads 16 consecutive rows with six 128-bit loads (4 x int4 image_idx, 1 x uint4
-//     class, 1 x uint4 active); a warp covers 512 consecutive rows, a CTA 8192.  The next
-//     block is prefetched into registers while the current one is tallied.
-//   * The CTA keeps a TILE x k int32 count tile in shared memory and tallies with shared-memory
-//     atomics.  Lanes are 16 rows apart, which spreads a warp over several images and keeps
-//     same-address conflicts low even when one class dominates an image.
-//   * When the stream leaves the tile, the tile is written to d_counts with coalesced stores
-//     (d_counts need not be zeroed) and reduced on the fly into the integer partials:
-//     class totals (64-bit shared accumulators), S2 = sum n_ij^2, R = sum n_i, images with
-//     n_i >= 1 / >= 2, sum n_i (n_i - 1).  Partials leave the CTA as 64-bit integer atomics, so
-//     they are exact and independent of scheduling and of the GPU count.
-//   * Every adjacent row pair is checked for order and every row for range; violations are
-//     reported in the partials (unsorted pairs; rows_seen != rows) — the host wrapper turns them
-//     into B2_ERR_NOT_SORTED / B2_ERR_BAD_ARG without the library having to synchronise.
+// tally_slab_kernel — rows ordered by image_idx (an index scan on id_img).  HBM-bound: 6 B read per row +
+//   4*k B written per image, every byte touched once; a thread per row, lanes a slab apart, shared-memory
+//   atomics into a sliding window of images (described in full above the kernel).  It replaced, in this order,
+//   a shared-atomic tile kernel, two warp-cooperative (ballot / MATCH.ANY) kernels and a thread-per-image
+//   kernel, all 3-4x slower (profiles/r1_tally_history.md).
 //
 // tally_scatter_kernel — any row order: global RED.ADD into a zeroed count matrix (bound by L2
 //   atomic throughput, not HBM), followed by the partials pass below.
@@ -40,7 +24,6 @@ namespace b2 {
 
 constexpr int kTallyThreads = 512;
 constexpr int kRowsPerThread = 16;
-constexpr int kBlockRows = kTallyThreads * kRowsPerThread;      // 8192
 constexpr int kTileBudgetBytes = 100 * 1024;                    // two CTAs per SM
 constexpr int kMaxTileImages = 512;
 
@@ -112,10 +95,6 @@ __device__ __noinline__ void flush_tile(int32_t *tile, uint32_t n_img, uint32_t 
     for (uint32_t e = threadIdx.x; e < elems; e += blockDim.x) tile[e] = 0;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-}
-
 struct RowBlock {
     int4 idx[4];
     uint4 cls, act;
@@ -163,670 +142,6 @@ __device__ __forceinline__ TallySmem carve_smem(uint8_t *raw, uint32_t tile_imag
     s.part = s.class_tot + k;
     s.dred = reinterpret_cast<double *>(s.part + 8);
     return s;
-}
-
-__global__ void __launch_bounds__(kTallyThreads, 2)
-tally_sorted_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
-                    const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
-                    uint32_t k, uint32_t tile_images, int32_t *__restrict__ counts,
-                    unsigned long long *__restrict__ g_partials) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    const TallySmem sm = carve_smem(smem_raw, tile_images, k);
-    int32_t *tile = sm.tile;
-
-    const uint32_t G = gridDim.x, b = blockIdx.x;
-    const int32_t img_end_all = image_base + int32_t(n_images);                  // host checked: fits int32
-    // nominal row range, aligned to the 16-row vector granule
-    const uint64_t nom0 = ((rows / G) * b + (rows % G) * b / G) & ~uint64_t(kRowsPerThread - 1);
-    const uint64_t nom1 = b + 1 == G ? rows : (((rows / G) * (b + 1) + (rows % G) * (b + 1) / G) & ~uint64_t(kRowsPerThread - 1));
-    // owned image range [I0, I1): the image under the nominal boundary row belongs to the CTA before
-    auto boundary = [&](uint64_t nom) -> int32_t {
-        const int32_t v = image_idx[nom];
-        return v < image_base ? image_base : (v >= img_end_all - 1 ? img_end_all : v + 1);
-    };
-    int32_t I0, I1;
-    if (rows == 0) {                                                             // nothing to stream: split the zero fill
-        I0 = image_base + int32_t(uint64_t(n_images) * b / G);
-        I1 = image_base + int32_t(uint64_t(n_images) * (b + 1) / G);
-    } else {
-        I0 = b == 0 ? image_base : boundary(nom0);
-        I1 = b + 1 == G ? img_end_all : boundary(nom1);
-        if (I1 < I0) I1 = I0;                                                    // unsorted input: own nothing
-    }
-
-    for (uint32_t e = threadIdx.x; e < tile_images * k; e += blockDim.x) tile[e] = 0;
-    for (uint32_t c = threadIdx.x; c < k + 8; c += blockDim.x) sm.class_tot[c] = 0;   // class totals + partials
-    __syncthreads();
-
-    int32_t base = I0;                                                           // first image of the tile
-    int32_t tile_end = I1 - base > int32_t(tile_images) ? base + int32_t(tile_images) : I1;
-    uint32_t rows_seen = 0, unsorted = 0;
-
-    auto flush = [&]() {                                                         // uniform
-        __syncthreads();
-        flush_tile<true, false>(tile, uint32_t(tile_end - base), k,
-                                counts + size_t(base - image_base) * k, sm.class_tot, sm.part, nullptr);
-        base = tile_end;
-        tile_end = I1 - base > int32_t(tile_images) ? base + int32_t(tile_images) : I1;
-        __syncthreads();
-    };
-
-    RowBlock cur;
-    uint64_t blk = nom0;
-    while (blk < rows) {
-        const uint64_t row0 = blk + uint64_t(threadIdx.x) * kRowsPerThread;
-        const uint64_t nblk = blk + kBlockRows;
-        load_rows(cur, image_idx, class_idx, active, row0, rows);
-        {   // pull the next block into L2 while this one is tallied (no registers held)
-            const uint64_t nrow0 = row0 + kBlockRows;
-            if (nrow0 < rows) {
-                prefetch_l2(image_idx + nrow0);
-                if ((threadIdx.x & 7) == 0) {                                     // one 128-byte line per 8 threads
-                    prefetch_l2(class_idx + nrow0);
-                    prefetch_l2(active + nrow0);
-                }
-            }
-        }
-
-        const int32_t ii[16] = {cur.idx[0].x, cur.idx[0].y, cur.idx[0].z, cur.idx[0].w, cur.idx[1].x, cur.idx[1].y,
-                                cur.idx[1].z, cur.idx[1].w, cur.idx[2].x, cur.idx[2].y, cur.idx[2].z, cur.idx[2].w,
-                                cur.idx[3].x, cur.idx[3].y, cur.idx[3].z, cur.idx[3].w};
-        const uint32_t cw[4] = {cur.cls.x, cur.cls.y, cur.cls.z, cur.cls.w};
-        const uint32_t aw[4] = {cur.act.x, cur.act.y, cur.act.z, cur.act.w};
-
-        // order check of every adjacent pair this CTA is responsible for: pairs (r-1, r) with
-        // nom0 <= r < nom1 (nom1 is a multiple of 16 or the table end, so a thread is all in or out)
-        if (row0 < nom1) {
-            int32_t prev = row0 > 0 ? __ldg(image_idx + row0 - 1) : INT32_MIN;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                unsorted += (ii[j] < prev) & (ii[j] != INT32_MIN);               // INT32_MIN = past the table
-                prev = ii[j];
-            }
-        }
-
-        bool any_mine = false;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) any_mine |= (ii[j] < I1) & (ii[j] != INT32_MIN);
-        for (;;) {
-            // Tile-relative counter index of each of my rows (kNoKey: not in this tile / bad class /
-            // inactive).  A thread's 16 rows are consecutive, so most share the image and its dominant
-            // class: rows equal to the first key are merged into ONE shared atomic, which removes most
-            // same-address conflicts between the lanes of a warp.
-            constexpr uint32_t kNoKey = 0xffffffffu;
-            bool beyond_tile = false;
-            auto key_of = [&](int j) -> uint32_t {
-                const int32_t img = ii[j];
-                const uint32_t c = (cw[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                const uint32_t a = (aw[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                const bool in_tile = (img >= base) & (img < tile_end) & (c < k);
-                return (in_tile && a) ? uint32_t(img - base) * k + c : kNoKey;
-            };
-            const uint32_t k0 = key_of(0);
-            uint32_t m = 0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int32_t img = ii[j];
-                const uint32_t c = (cw[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                rows_seen += (img >= base) & (img < tile_end) & (c < k);
-                beyond_tile |= (img >= tile_end) & (img < I1);
-                m += key_of(j) == k0;
-            }
-            if (k0 != kNoKey) atomicAdd(&tile[k0], int32_t(m));
-#pragma unroll
-            for (int j = 1; j < 16; ++j) {
-                const uint32_t kj = key_of(j);
-                if (kj != k0 && kj != kNoKey) atomicAdd(&tile[kj], 1);
-            }
-            if (!__syncthreads_or(beyond_tile)) break;
-            flush();                                                             // tile complete: write it, open the next
-        }
-        // the stream has left this CTA's images once a whole block past the nominal end is foreign
-        const bool stream_live = __syncthreads_or(any_mine) || nblk < nom1;
-        if (!stream_live) break;
-        blk = nblk;
-    }
-    // remaining tiles (the open one and any image range without rows)
-    while (base < I1) flush();
-    part_add(sm.part, P_ROWS_SEEN, rows_seen);
-    part_add(sm.part, P_UNSORTED, unsorted);
-    __syncthreads();
-    commit_partials(sm.part, sm.class_tot, k, g_partials);
-}
-
-// ----------------------------------------------------------------------------------------
-// tally_warp_kernel — the product kernel for rows ordered by image_idx.  No atomics on the row
-// path at all (measured: shared-memory atomics cost ~2 cycles per lane and bound the tile
-// kernel above at 22 % of HBM peak):
-//   * A WARP streams a contiguous row range and owns the images that START in it (same
-//     ownership rule as above, per warp instead of per CTA).
-//   * Rows reach the warp through its own ring of two shared-memory stages of 256 rows filled by
-//     the bulk-copy (TMA) engine (cp.async.bulk + mbarrier, three 1-D copies per stage issued by
-//     one lane): the next stage is in flight while this one is tallied, without holding registers.
-//   * A step is 32 consecutive rows, one per lane.  MATCH.ANY on the class byte gives every lane
-//     the set of lanes with its class; ANDed with the ballot of "active, in range, current
-//     image" it is the group whose size is the increment.  The lowest lane of each group adds
-//     it to the warp's PRIVATE k-entry counter array in shared memory with a plain
-//     read-modify-write: groups have distinct classes, so there are no conflicts and no atomics.
-//   * When the image changes the lanes copy the k counters to d_counts — one coalesced k*4-byte
-//     store per image, no tile, no flush — zero them and fold them into per-warp class totals
-//     and the sum of squares.  n_i is the population count of the row mask, uniform across the
-//     warp, so R, rated images and pairs need no reduction.
-//   * Partials are combined per CTA in shared memory, then one 64-bit atomic per value and CTA.
-// ----------------------------------------------------------------------------------------
-constexpr int kWarpKernelThreads = 256;
-constexpr int kWarpsPerCta = kWarpKernelThreads / 32;
-constexpr int kStageRows = 256;
-constexpr int kGroupRows = kStageRows;                        // nominal starts are aligned to one stage
-constexpr int kStageBytes = kStageRows * 6;                   // int32 image + uint8 class + uint8 active
-constexpr int kStages = 2;
-constexpr int kWarpSmemBytes = kStages * kStageBytes + 256 * 4 + 256 * 8;            // ring + counters + class totals
-constexpr int kWarpKernelSmem = kWarpsPerCta * kWarpSmemBytes;                       // 48 KB per CTA, four CTAs per SM
-
-__global__ void __launch_bounds__(kWarpKernelThreads, 4)
-tally_warp_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
-                  const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
-                  uint32_t k, uint64_t n_workers, int32_t *__restrict__ counts,
-                  unsigned long long *__restrict__ g_partials) {
-    __shared__ unsigned long long s_tot[256 + 8];
-    extern __shared__ __align__(128) uint8_t warp_smem[];
-    __shared__ __align__(8) uint64_t ring_bars[kWarpsPerCta * kStages];
-    for (uint32_t i = threadIdx.x; i < 256 + 8; i += blockDim.x) s_tot[i] = 0;
-
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint8_t *my = warp_smem + size_t(wid) * kWarpSmemBytes;
-    uint32_t *cnt_s = reinterpret_cast<uint32_t *>(my + kStages * kStageBytes);             // k counters of image `cur`
-    unsigned long long *tot_s = reinterpret_cast<unsigned long long *>(my + kStages * kStageBytes + 256 * 4);
-    for (uint32_t c = lane; c < 256; c += 32) { cnt_s[c] = 0; tot_s[c] = 0; }
-    __syncthreads();
-
-    // n_workers warps share the rows; the host keeps it <= rows/512 so that nominal starts are distinct
-    const uint64_t W = n_workers;
-    const uint64_t w = uint64_t(blockIdx.x) * kWarpsPerCta + wid;
-    const bool worker = w < W;
-    const int32_t img_end_all = image_base + int32_t(n_images);
-    auto nominal = [&](uint64_t i) -> uint64_t {
-        return i >= W ? rows : (((rows / W) * i + (rows % W) * i / W) & ~uint64_t(kGroupRows - 1));
-    };
-    const uint64_t nom0 = nominal(w), nom1 = nominal(w + 1);
-    auto boundary = [&](uint64_t nom) -> int32_t {
-        const int32_t v = __ldg(image_idx + nom);
-        return v < image_base ? image_base : (v >= img_end_all - 1 ? img_end_all : v + 1);
-    };
-    int32_t I0, I1;
-    if (!worker) {
-        I0 = I1 = img_end_all;                                // spare warp of the last CTA: owns nothing
-    } else if (rows == 0) {
-        I0 = image_base + int32_t(uint64_t(n_images) * w / W);
-        I1 = image_base + int32_t(uint64_t(n_images) * (w + 1) / W);
-    } else {
-        I0 = w == 0 ? image_base : boundary(nom0);
-        I1 = w + 1 == W ? img_end_all : boundary(nom1);
-        if (I1 < I0) I1 = I0;                                 // unsorted input
-    }
-    const int32_t span = I1 - I0;                             // "mine" <=> unsigned(img - I0) < span
-    const uint32_t lanes_below = (1u << lane) - 1u;
-
-    unsigned long long s2 = 0, sum_r = 0, pairs = 0;
-    uint32_t rated = 0, pair_images = 0, seen = 0, unsorted = 0, n_cur = 0;
-    int32_t cur = I0;
-
-    // store the finished image, fold it into the partials, zero-fill images without rows up to `next`
-    auto finish_image = [&](int32_t next) {
-        __syncwarp();
-        if (cur < I1) {
-            int32_t *dst = counts + size_t(cur - image_base) * k;
-            for (uint32_t c = lane; c < k; c += 32) {
-                const uint32_t v = cnt_s[c];
-                dst[c] = int32_t(v);
-                if (v) {
-                    cnt_s[c] = 0;
-                    tot_s[c] += v;
-                    s2 += (unsigned long long)v * v;
-                }
-            }
-            sum_r += n_cur;
-            rated += n_cur >= 1;
-            pair_images += n_cur >= 2;
-            pairs += (unsigned long long)n_cur * (n_cur - (n_cur > 0));
-            n_cur = 0;
-            const int32_t stop = next < I1 ? next : I1;
-            for (int32_t img = cur + 1; img < stop; ++img) {
-                int32_t *z = counts + size_t(img - image_base) * k;
-                for (uint32_t c = lane; c < k; c += 32) z[c] = 0;
-            }
-        }
-        cur = next;
-        __syncwarp();
-    };
-
-    // add the rows of `vm` (a ballot: rows of image `cur` that count) to the warp's counters
-    auto accumulate = [&](uint32_t same_class, uint32_t vm, uint32_t c) {
-        const uint32_t grp = same_class & vm;                 // rows with my class that count
-        if (((vm >> lane) & 1u) && (grp & lanes_below) == 0) cnt_s[c] += __popc(grp);   // lowest lane of the group
-        n_cur += __popc(vm);
-    };
-
-    // one step of 32 consecutive rows; returns false once the stream has left this warp's images
-    auto step = [&](int32_t img, uint32_t c, uint32_t act, int32_t prev_img, bool check_order) -> bool {
-        if (check_order) {
-            // lane l > 0 compares with lane l-1 of this step, lane 0 with lane 31 of the previous one
-            const int32_t z = lane == 31 ? prev_img : img;
-            const int32_t before = __shfl_sync(0xffffffffu, z, (lane + 31) & 31);
-            unsorted += (img < before) & (img != INT32_MAX);
-        }
-        if (span <= 0) return false;                          // this warp owns no image: order check only
-        const uint32_t same_class = __match_any_sync(0xffffffffu, c);
-        const bool good = (c < k) & (act != 0);
-        if (__all_sync(0xffffffffu, img == cur)) {            // common case: one image, the current one
-            seen += c < k;
-            accumulate(same_class, __ballot_sync(0xffffffffu, good), c);
-            __syncwarp();
-            return true;
-        }
-        const bool mine = uint32_t(img - I0) < uint32_t(span);
-        seen += mine & (c < k);
-        uint32_t rem = __ballot_sync(0xffffffffu, mine);
-        while (rem) {
-            const int first = __ffs(rem) - 1;
-            const int32_t nxt = __shfl_sync(0xffffffffu, img, first);
-            if (nxt != cur) finish_image(nxt);
-            const uint32_t same = __ballot_sync(0xffffffffu, img == nxt) & rem;
-            accumulate(same_class, __ballot_sync(0xffffffffu, mine & good & (img == nxt)), c);
-            __syncwarp();
-            rem &= ~same;
-        }
-        return __any_sync(0xffffffffu, img < I1) != 0;
-    };
-
-    if (worker && nom0 < rows && span >= 0) {
-        int32_t *s_idx = reinterpret_cast<int32_t *>(my);
-        uint64_t *bars = ring_bars + wid * kStages;
-        auto stage_idx = [&](int b) { return s_idx + b * (kStageBytes / 4); };
-        auto stage_cls = [&](int b) { return reinterpret_cast<uint8_t *>(stage_idx(b)) + kStageRows * 4; };
-        auto stage_act = [&](int b) { return stage_cls(b) + kStageRows; };
-        if (lane == 0) {
-#pragma unroll
-            for (int b = 0; b < kStages; ++b) mbar_init(&bars[b], 1);
-            fence_mbar_init();
-        }
-        __syncwarp();
-        const uint64_t n_stage = (rows - nom0 + kStageRows - 1) / kStageRows;    // upper bound; the stream usually ends earlier
-        auto issue = [&](uint64_t st) {                       // whole warp calls; lane 0 issues
-            const uint64_t r0 = nom0 + st * kStageRows;
-            const int b = int(st % kStages);
-            if (r0 + kStageRows <= rows) {
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&bars[b], kStageRows * 6);
-                    bulk_g2s(stage_idx(b), image_idx + r0, kStageRows * 4, &bars[b]);
-                    bulk_g2s(stage_cls(b), class_idx + r0, kStageRows, &bars[b]);
-                    bulk_g2s(stage_act(b), active + r0, kStageRows, &bars[b]);
-                }
-            } else {                                          // ragged end of the table: plain loads, sentinel fill
-                for (int i = lane; i < kStageRows; i += 32) {
-                    const bool in = r0 + i < rows;
-                    stage_idx(b)[i] = in ? image_idx[r0 + i] : INT32_MAX;        // sorts last, owned by nobody
-                    stage_cls(b)[i] = in ? class_idx[r0 + i] : uint8_t(0);
-                    stage_act(b)[i] = in ? active[r0 + i] : uint8_t(0);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[b]);
-            }
-        };
-        int32_t prev_img = nom0 > 0 ? __ldg(image_idx + nom0 - 1) : INT32_MIN;   // row before the first
-        const bool owns = span > 0;
-        uint64_t issued = 0, st = 0;
-        for (; issued < kStages - 1 && issued < n_stage; ++issued) issue(issued);
-        for (; st < n_stage; ++st) {
-            if (issued < n_stage) { issue(issued); ++issued; }
-            const int b = int(st % kStages);
-            mbar_wait(&bars[b], uint32_t((st / kStages) & 1));
-            const int32_t *si = stage_idx(b) + lane;
-            const uint8_t *sc = stage_cls(b) + lane, *sa = stage_act(b) + lane;
-            const uint64_t r0 = nom0 + st * kStageRows;
-            const bool check_order = r0 < nom1;               // nom1 is stage aligned (or the table end)
-            bool any_mine = false;
-#pragma unroll 4
-            for (int t = 0; t < kStageRows / 32; ++t) {
-                const int32_t img = si[32 * t];
-                any_mine |= step(img, sc[32 * t], sa[32 * t], prev_img, check_order);
-                prev_img = img;
-            }
-            __syncwarp();                                     // every lane is done with this stage before it is refilled
-            // past the nominal end with nothing below I1 in this stage: the stream has left my images
-            if (r0 + kStageRows >= nom1 && !(any_mine && owns)) { ++st; break; }
-        }
-        // stages issued but not consumed: their copies must land before this CTA's shared memory is released
-        for (; st < issued; ++st) mbar_wait(&bars[st % kStages], uint32_t((st / kStages) & 1));
-    }
-    finish_image(I1);
-
-    // ---- commit: warp -> CTA (shared, 64-bit) -> global (one atomic per value and CTA) ----
-    for (uint32_t c = lane; c < k; c += 32)
-        if (tot_s[c]) atomicAdd(&s_tot[c], tot_s[c]);
-    {
-        const unsigned long long v_s2 = warp_sum(s2), v_seen = warp_sum(seen), v_uns = warp_sum(unsorted);
-        if (lane == 0) {
-            if (v_s2) atomicAdd(&s_tot[256 + P_S2], v_s2);
-            if (sum_r) atomicAdd(&s_tot[256 + P_R], sum_r);
-            if (rated) atomicAdd(&s_tot[256 + P_RATED], (unsigned long long)rated);
-            if (pair_images) atomicAdd(&s_tot[256 + P_PAIR_IMAGES], (unsigned long long)pair_images);
-            if (pairs) atomicAdd(&s_tot[256 + P_PAIRS], pairs);
-            if (v_seen) atomicAdd(&s_tot[256 + P_ROWS_SEEN], v_seen);
-            if (v_uns) atomicAdd(&s_tot[256 + P_UNSORTED], v_uns);
-        }
-    }
-    __syncthreads();
-    for (uint32_t c = threadIdx.x; c < k; c += blockDim.x)
-        if (s_tot[c]) atomicAdd(&g_partials[c], s_tot[c]);
-    if (threadIdx.x < 7 && s_tot[256 + threadIdx.x]) atomicAdd(&g_partials[k + threadIdx.x], s_tot[256 + threadIdx.x]);
-}
-
-// ----------------------------------------------------------------------------------------
-// tally_image_kernel — thread-per-image formulation for rows ordered by image_idx.
-// The warp kernel above spends ~108 warp-instructions per 32 rows because the whole warp cooperates on
-// each row group.  Here every THREAD tallies a whole image by itself, so the SIMT width is used on
-// independent rows: ~10 thread-instructions per row.
-//   * CTA b owns the images that START in its nominal row range (same rule as above) and walks them in
-//     tiles of `tile_images` images whose counters (int32, row pitch k|1 so a column walk is
-//     conflict-free) live in shared memory.
-//   * Phase A (coalesced): blocks of 4096 rows, 16 consecutive rows per thread (six 128-bit loads).
-//     Each row becomes ONE byte in a shared row buffer — its class, or 0xFF when inactive / foreign /
-//     out of range — and every image change records where the image's rows start and end in that
-//     buffer.  Order and range checks happen here.  A phase ends when the buffer is full or the stream
-//     leaves the tile.
-//   * Phase B: thread i walks the rows [start_i, end_i) of image tile_base+i in the row buffer and
-//     increments its own counters with plain read-modify-writes: no atomics, no warp collectives.
-//   * A finished tile is written to d_counts with coalesced stores and folded into the integer
-//     partials exactly like the other kernels.
-// ----------------------------------------------------------------------------------------
-constexpr int kImgThreads = 256;
-constexpr int kImgBlockRows = kImgThreads * kRowsPerThread;       // 4096
-constexpr uint32_t kNoRow = 0xffffffffu;
-
-struct ImgSmem {
-    int32_t *cnt;                 // tile_images * pitch
-    uint8_t *rowbuf;              // cap_rows
-    uint32_t *seg_start, *seg_end;// tile_images each
-    unsigned long long *class_tot;// k
-    unsigned long long *part;     // 8
-    uint32_t *first_beyond;       // 1 (row offset in the buffer of the first row past the tile)
-    uint32_t *tile_tot;           // k (class totals of the open tile, 32-bit)
-};
-__host__ __device__ inline size_t img_smem_layout(uint32_t tile_images, uint32_t pitch, uint32_t cap_rows, uint32_t k,
-                                                  size_t *o_rowbuf, size_t *o_seg, size_t *o_tot) {
-    size_t off = (size_t(tile_images) * pitch * 4 + 15) & ~size_t(15);
-    *o_rowbuf = off; off += (size_t(cap_rows) + 15) & ~size_t(15);
-    *o_seg = off; off += size_t(tile_images) * 8;
-    off = (off + 7) & ~size_t(7);
-    *o_tot = off; off += size_t(k) * 8 + 8 * 8 + 16 + size_t(k) * 4;
-    return off;
-}
-
-__global__ void __launch_bounds__(kImgThreads, 3)
-tally_image_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
-                   const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
-                   uint32_t k, uint32_t tile_images, uint32_t cap_rows, int32_t *__restrict__ counts,
-                   unsigned long long *__restrict__ g_partials) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    const uint32_t pitch = k | 1u;
-    size_t o_rowbuf, o_seg, o_tot;
-    img_smem_layout(tile_images, pitch, cap_rows, k, &o_rowbuf, &o_seg, &o_tot);
-    ImgSmem sm;
-    sm.cnt = reinterpret_cast<int32_t *>(smem_raw);
-    sm.rowbuf = smem_raw + o_rowbuf;
-    sm.seg_start = reinterpret_cast<uint32_t *>(smem_raw + o_seg);
-    sm.seg_end = sm.seg_start + tile_images;
-    sm.class_tot = reinterpret_cast<unsigned long long *>(smem_raw + o_tot);
-    sm.part = sm.class_tot + k;
-    sm.first_beyond = reinterpret_cast<uint32_t *>(sm.part + 8);
-    sm.tile_tot = sm.first_beyond + 4;
-    const uint32_t tid = threadIdx.x;
-
-    const uint32_t G = gridDim.x, b = blockIdx.x;
-    const int32_t img_end_all = image_base + int32_t(n_images);
-    auto nominal = [&](uint64_t i) -> uint64_t {
-        return i >= G ? rows : (((rows / G) * i + (rows % G) * i / G) & ~uint64_t(kRowsPerThread - 1));
-    };
-    const uint64_t nom0 = nominal(b), nom1 = nominal(b + 1);
-    auto boundary = [&](uint64_t nom) -> int32_t {
-        const int32_t v = __ldg(image_idx + nom);
-        return v < image_base ? image_base : (v >= img_end_all - 1 ? img_end_all : v + 1);
-    };
-    int32_t I0, I1;
-    if (rows == 0) {
-        I0 = image_base + int32_t(uint64_t(n_images) * b / G);
-        I1 = image_base + int32_t(uint64_t(n_images) * (b + 1) / G);
-    } else {
-        I0 = b == 0 ? image_base : boundary(nom0);
-        I1 = b + 1 == G ? img_end_all : boundary(nom1);
-        if (I1 < I0) I1 = I0;
-    }
-
-    for (uint32_t e = tid; e < tile_images * pitch; e += blockDim.x) sm.cnt[e] = 0;
-    for (uint32_t i = tid; i < tile_images; i += blockDim.x) { sm.seg_start[i] = 0; sm.seg_end[i] = 0; }
-    for (uint32_t c = tid; c < k + 8; c += blockDim.x) sm.class_tot[c] = 0;
-    for (uint32_t c = tid; c < k; c += blockDim.x) sm.tile_tot[c] = 0;
-    if (tid == 0) *sm.first_beyond = kNoRow;
-    __syncthreads();
-
-    uint32_t seen = 0, unsorted = 0;
-    int32_t tb = I0;                                                         // first image of the open tile
-    int32_t tile_end = I1 - tb > int32_t(tile_images) ? tb + int32_t(tile_images) : I1;
-
-    // write the open tile, fold it into the partials, zero it, open the next one (uniform)
-    auto flush = [&]() {
-        __syncthreads();
-        const uint32_t n_img = uint32_t(tile_end - tb);
-        int32_t *dst = counts + size_t(tb - image_base) * k;
-        unsigned long long s2 = 0;
-        // element order: coalesced stores, class totals, sum of squares
-        uint32_t i = tid / k, c = tid - i * k;
-        const uint32_t di = blockDim.x / k, dc = blockDim.x - di * k;
-        for (uint32_t e = tid; e < n_img * k; e += blockDim.x) {
-            const uint32_t v = uint32_t(sm.cnt[i * pitch + c]);
-            dst[e] = int32_t(v);
-            if (v) {
-                s2 += (unsigned long long)v * v;
-                atomicAdd(&sm.tile_tot[c], v);                              // native 32-bit shared atomic; a tile holds < 2^32 ratings
-            }
-            i += di; c += dc;
-            if (c >= k) { c -= k; ++i; }
-        }
-        // one thread per image: n_i and what derives from it (pitch is odd: conflict-free)
-        unsigned long long r = 0, pairs = 0, rated = 0, pair_images = 0;
-        for (uint32_t im = tid; im < n_img; im += blockDim.x) {
-            const int32_t *row = sm.cnt + im * pitch;
-            unsigned long long n = 0;
-            for (uint32_t j = 0; j < k; ++j) n += uint32_t(row[j]);
-            r += n; rated += n >= 1; pair_images += n >= 2; pairs += n * (n - (n > 0));
-        }
-        part_add(sm.part, P_S2, s2);
-        part_add(sm.part, P_R, r);
-        part_add(sm.part, P_RATED, rated);
-        part_add(sm.part, P_PAIR_IMAGES, pair_images);
-        part_add(sm.part, P_PAIRS, pairs);
-        __syncthreads();
-        for (uint32_t c2 = tid; c2 < k; c2 += blockDim.x) {                  // fold the tile's class totals into 64 bits
-            sm.class_tot[c2] += sm.tile_tot[c2];
-            sm.tile_tot[c2] = 0;
-        }
-        for (uint32_t e = tid; e < n_img * pitch; e += blockDim.x) sm.cnt[e] = 0;
-        tb = tile_end;
-        tile_end = I1 - tb > int32_t(tile_images) ? tb + int32_t(tile_images) : I1;
-        __syncthreads();
-    };
-
-    uint64_t consume_from = nom0;                                            // first row not yet tallied (uniform)
-    bool stream_done = rows == 0 || nom0 >= rows;
-    while (!stream_done) {
-        // ---------------- phase A: fill the row buffer ----------------
-        const uint64_t buf_row0 = consume_from & ~uint64_t(kRowsPerThread - 1);
-        // number of 4096-row blocks this phase may buffer (uniform), and where they end
-        uint32_t n_blk = cap_rows / kImgBlockRows;
-        {
-            const uint64_t left = (rows - buf_row0 + kImgBlockRows - 1) / kImgBlockRows;
-            if (left < n_blk) n_blk = uint32_t(left);
-        }
-        const uint64_t loaded_end = buf_row0 + uint64_t(n_blk) * kImgBlockRows < rows
-                                        ? buf_row0 + uint64_t(n_blk) * kImgBlockRows : rows;
-        auto process = [&](const RowBlock &rbk, uint64_t row0) {
-            const int32_t ii[16] = {rbk.idx[0].x, rbk.idx[0].y, rbk.idx[0].z, rbk.idx[0].w, rbk.idx[1].x, rbk.idx[1].y,
-                                    rbk.idx[1].z, rbk.idx[1].w, rbk.idx[2].x, rbk.idx[2].y, rbk.idx[2].z, rbk.idx[2].w,
-                                    rbk.idx[3].x, rbk.idx[3].y, rbk.idx[3].z, rbk.idx[3].w};
-            const uint32_t cw[4] = {rbk.cls.x, rbk.cls.y, rbk.cls.z, rbk.cls.w};
-            const uint32_t aw[4] = {rbk.act.x, rbk.act.y, rbk.act.z, rbk.act.w};
-            int32_t prev = (row0 > 0 && row0 <= rows) ? __ldg(image_idx + row0 - 1) : INT32_MIN;
-            uint32_t packed[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-            const uint32_t off0 = uint32_t(row0 - buf_row0);
-            // Common path: all 16 rows exist, are new to this phase and lie in the open tile (rows are ordered,
-            // so the first and the last decide).  The 16 class bytes are merged with the active / range masks
-            // four at a time; image changes are rare (one per ~100 rows), so each row costs one compare and a
-            // short, rarely taken block that records where the images start and end in the row buffer.  Only
-            // threads at the edges of a phase or of a tile take the general path below: divergence is
-            // confined to the one or two warps that hold such an edge.
-            if (row0 > consume_from && row0 + kRowsPerThread <= rows && ii[0] >= tb && ii[15] < tile_end &&
-                prev <= ii[0]) {
-                const uint32_t n_tile = uint32_t(tile_end - tb);
-                const uint32_t k4 = k >= 256 ? 0u : k * 0x01010101u;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t in_range = k >= 256 ? 0xffffffffu : __vcmpltu4(cw[w], k4);
-                    const uint32_t keep = in_range & __vcmpne4(aw[w], 0u);
-                    packed[w] = (cw[w] & keep) | ~keep;
-                    seen += __popc(in_range) >> 3;
-                }
-                *reinterpret_cast<uint4 *>(sm.rowbuf + off0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                const bool count_order = row0 + kRowsPerThread <= nom1;      // nom1 is 16-aligned: all rows or none
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int32_t img = ii[j];
-                    if (img != prev) {
-                        if (count_order) unsorted += img < prev;
-                        const uint32_t rel = uint32_t(img - tb), relp = uint32_t(prev - tb);
-                        if (rel < n_tile) sm.seg_start[rel] = off0 + j;
-                        if (relp < n_tile) sm.seg_end[relp] = off0 + j;
-                    }
-                    prev = img;
-                }
-                return;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint64_t row = row0 + j;
-                const int32_t img = ii[j];
-                const bool valid = row < rows && row >= consume_from;        // exists and not tallied in an earlier phase
-                const uint32_t c = (cw[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                const uint32_t a = (aw[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                if (valid) {
-                    if (row < nom1) unsorted += img < prev;                  // pairs (r-1, r), nom0 <= r < nom1
-                    const bool in_tile = (img >= tb) & (img < tile_end);
-                    const bool first_here = (img != prev) | (row == consume_from);
-                    if (in_tile) {
-                        seen += c < k;
-                        if (a && c < k) packed[j >> 2] = (packed[j >> 2] & ~(0xffu << (8 * (j & 3)))) | (c << (8 * (j & 3)));
-                        if (first_here) sm.seg_start[img - tb] = off0 + j;
-                    } else if (img >= tile_end && first_here && (prev < tile_end || row == consume_from)) {
-                        atomicMin(sm.first_beyond, off0 + j);                // the stream leaves the tile here
-                    }
-                    if (img != prev && row > consume_from && prev >= tb && prev < tile_end)
-                        sm.seg_end[prev - tb] = off0 + j;                    // the previous image's rows end here
-                }
-                prev = img;
-            }
-            *reinterpret_cast<uint4 *>(sm.rowbuf + off0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        };
-        // Software pipeline: the loads of block nb+1 are in flight while block nb is scanned; no barrier
-        // between blocks.  Rows are ordered, so the image of a block's LAST row tells every thread alike
-        // whether the stream leaves the tile inside that block: if it does, nothing further is loaded.
-        {
-            RowBlock q[2];
-            const uint64_t trow = uint64_t(tid) * kRowsPerThread;
-            auto last_img_of = [&](uint32_t cb) -> int32_t {
-                const uint64_t end = buf_row0 + uint64_t(cb + 1) * kImgBlockRows;
-                return __ldg(image_idx + (end < rows ? end : rows) - 1);
-            };
-            int32_t last_img = 0, next_last = 0;
-            if (n_blk) { load_rows(q[0], image_idx, class_idx, active, buf_row0 + trow, rows); last_img = last_img_of(0); }
-            for (uint32_t nb = 0; nb < n_blk; nb += 2) {
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const uint32_t cb = nb + u;
-                    if (cb < n_blk) {
-                        const uint64_t blk = buf_row0 + uint64_t(cb) * kImgBlockRows;
-                        const bool more = cb + 1 < n_blk && last_img < tile_end;
-                        if (more) {
-                            load_rows(q[u ^ 1], image_idx, class_idx, active, blk + kImgBlockRows + trow, rows);
-                            next_last = last_img_of(cb + 1);
-                        }
-                        process(q[u], blk + trow);
-                        last_img = next_last;
-                        if (!more) nb = n_blk;                               // leave both loops after this block
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        const uint32_t fb = *sm.first_beyond;
-        const uint64_t stop = fb != kNoRow ? buf_row0 + fb : loaded_end;     // first row NOT tallied by this phase
-        if (tid == 0 && stop > consume_from) {                               // close the last image of the buffer
-            const int32_t li = __ldg(image_idx + stop - 1);
-            if (li >= tb && li < tile_end) sm.seg_end[li - tb] = uint32_t(stop - buf_row0);
-        }
-        __syncthreads();
-        // ---------------- phase B: one thread per image ----------------
-        const uint32_t n_tile = uint32_t(tile_end - tb);
-        for (uint32_t im = tid; im < n_tile; im += blockDim.x) {
-            const uint32_t s = sm.seg_start[im], e = sm.seg_end[im];
-            int32_t *my = sm.cnt + im * pitch;
-            uint32_t r = s;
-            for (; r + 4 <= e; r += 4) {          // four row bytes first, then the counter updates: the loads
-                const uint32_t m0 = sm.rowbuf[r], m1 = sm.rowbuf[r + 1], m2 = sm.rowbuf[r + 2], m3 = sm.rowbuf[r + 3];
-                if (m0 != 0xffu) my[m0] += 1;     // do not wait behind the stores
-                if (m1 != 0xffu) my[m1] += 1;
-                if (m2 != 0xffu) my[m2] += 1;
-                if (m3 != 0xffu) my[m3] += 1;
-            }
-            for (; r < e; ++r) {
-                const uint32_t m = sm.rowbuf[r];
-                if (m != 0xffu) my[m] += 1;
-            }
-            sm.seg_start[im] = 0;
-            sm.seg_end[im] = 0;
-        }
-        if (tid == 0) *sm.first_beyond = kNoRow;
-        consume_from = stop;
-        // the tile is complete when the stream left it (or ended); the stream is over for this CTA when it
-        // ended or when the next row belongs to somebody else's images
-        const bool left_tile = fb != kNoRow || stop >= rows;
-        bool next_foreign = stop >= rows;
-        if (!next_foreign && fb != kNoRow) next_foreign = __ldg(image_idx + stop) >= I1;
-        if (left_tile) {
-            if (tb < I1) flush(); else __syncthreads();
-            if (!next_foreign) {                                             // tiles without any row: write zeros, no reload
-                const int32_t ni = __ldg(image_idx + stop);
-                while (tb < I1 && ni >= tile_end) flush();
-            }
-            if (next_foreign) {
-                // order check still has to reach nom1 when this CTA's images end early (unsorted input only)
-                stream_done = true;
-            } else if (tb >= I1) {
-                stream_done = true;
-            }
-        } else {
-            __syncthreads();
-        }
-    }
-    // remaining tiles (image ranges without rows), then the order check of rows this CTA did not stream
-    while (tb < I1) flush();
-    for (uint64_t r = (consume_from > nom0 ? consume_from : nom0) + tid; r < nom1 && r < rows; r += blockDim.x) {
-        const int32_t prev = r > 0 ? __ldg(image_idx + r - 1) : INT32_MIN;
-        unsorted += __ldg(image_idx + r) < prev;
-    }
-    part_add(sm.part, P_ROWS_SEEN, seen);
-    part_add(sm.part, P_UNSORTED, unsorted);
-    __syncthreads();
-    commit_partials(sm.part, sm.class_tot, k, g_partials);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1267,13 +582,6 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
 
 }  // namespace b2
 
-// B2_TALLY_PATH: unset = auto (slab kernel; warp kernel for >= 512 rows per image), 0 = thread-per-image kernel,
-// 1 = MATCH.ANY warp kernel, 2 = shared-atomic tile kernel, 3 = thread-per-row slab kernel.
-static int tally_path_override() {
-    const char *e = getenv("B2_TALLY_PATH");
-    return e ? atoi(e) : -1;
-}
-
 extern "C" uint64_t b2_label_tally_workspace_bytes(uint32_t n_images) {
     (void)n_images;
     return 0;
@@ -1304,101 +612,37 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
     B2_CUDA_CHECK(cudaMemsetAsync(partials, 0, (size_t(k) + B2_PARTIALS_EXTRA) * 8, st));
     const uint32_t tile_images = pick_tile_images(k);
     const size_t smem = tally_smem_bytes(tile_images, k);
-    if (flags & B2_TALLY_SORTED) {
-        // Auto: the slab kernel keeps the lanes of a warp in different images as long as an image has fewer rows
-        // than a slab; images with very many rows go to the warp kernel (whose common case is "32 rows of the
-        // same image").  The other two kernels stay selectable for comparison (profiles/r1_tally_history.md).
-        int path = tally_path_override();
-        if (path < 0) path = (rows / n_images >= 512) ? 1 : 3;
-        if (path == 0) {                                     // thread-per-image kernel
-            const uint32_t pitch = k | 1u;
-            uint32_t ti = 192, cap = 20480;                 // 39 KB counters (k = 50) + 20 KB rows: three CTAs per SM
-            if (const char *e = getenv("B2_TALLY_TILE")) ti = uint32_t(atoi(e));
-            if (const char *e = getenv("B2_TALLY_CAP")) cap = uint32_t(atoi(e));
-            const uint32_t by_smem = (56u * 1024u) / (pitch * 4u);           // counters <= 56 KB
-            if (ti > by_smem) ti = by_smem;
-            if (ti < 1) ti = 1;
-            cap = cap / kImgBlockRows * kImgBlockRows;
-            if (cap < uint32_t(kImgBlockRows)) cap = kImgBlockRows;
-            size_t o1, o2, o3;
-            const size_t smem_img = img_smem_layout(ti, pitch, cap, k, &o1, &o2, &o3);
-            B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_image_kernel), smem_img));
-            int per_sm = int((220u * 1024u) / (smem_img + 1024));
-            if (per_sm > 4) per_sm = 4;
-            if (per_sm < 1) per_sm = 1;
-            uint64_t want = rows ? (rows + 4ull * kImgBlockRows - 1) / (4ull * kImgBlockRows)
-                                 : (uint64_t(n_images) + ti - 1) / ti;
-            const uint64_t cap_ctas = uint64_t(per_sm) * uint64_t(sm_count());
-            if (want > cap_ctas) want = cap_ctas;
-            if (want < 1) want = 1;
-            tally_image_kernel<<<uint32_t(want), kImgThreads, smem_img, st>>>(d_image_idx, d_class_idx, d_active, rows,
-                                                                             int32_t(image_base), n_images, k, ti, cap,
-                                                                             d_counts, partials);
-            B2_LAUNCH_CHECK("tally_image_kernel");
+    if (flags & B2_TALLY_SORTED) {                           // thread-per-row slab kernel
+        uint32_t stages = 3, per_sm = 2;
+        if (const char *e = getenv("B2_TALLY_STAGES")) stages = atoi(e) == 2 ? 2u : 3u;
+        if (const char *e = getenv("B2_TALLY_CTAS")) per_sm = uint32_t(atoi(e)) < 1 ? 1u : uint32_t(atoi(e));
+        const size_t budget = (227u * 1024u) / per_sm - 1024u;               // per CTA, incl. the 1 KB the driver reserves
+        uint32_t t = 0;
+        while (t < 13 && slab_smem_bytes(stages, 2u << t, k) <= budget) ++t;
+        if (const char *e = getenv("B2_TALLY_TILE_LOG2")) t = uint32_t(atoi(e));
+        const size_t smem_slab = slab_smem_bytes(stages, 1u << t, k);
+        uint64_t want = rows ? (rows + 2ull * kSlabStageRows - 1) / (2ull * kSlabStageRows)
+                             : (uint64_t(n_images) + 1023) / 1024;
+        const uint64_t cap_ctas = uint64_t(per_sm) * uint64_t(sm_count());
+        if (want > cap_ctas) want = cap_ctas;
+        if (want < 1) want = 1;
+        auto launch = [&](auto kern) -> int {
+            B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(kern), smem_slab));
+            kern<<<uint32_t(want), kSlabThreads, smem_slab, st>>>(d_image_idx, d_class_idx, d_active, rows,
+                                                                 int32_t(image_base), n_images, k, t, d_counts, partials);
+            B2_LAUNCH_CHECK("tally_slab_kernel");
             return B2_OK;
+        };
+        if (stages == 2) {
+            if (k <= 32) return launch(tally_slab_kernel<1, 2>);
+            if (k <= 64) return launch(tally_slab_kernel<2, 2>);
+            if (k <= 128) return launch(tally_slab_kernel<4, 2>);
+            return launch(tally_slab_kernel<8, 2>);
         }
-        if (path == 3) {                                     // thread-per-row slab kernel
-            uint32_t stages = 3, per_sm = 2;
-            if (const char *e = getenv("B2_TALLY_STAGES")) stages = atoi(e) == 2 ? 2u : 3u;
-            if (const char *e = getenv("B2_TALLY_CTAS")) per_sm = uint32_t(atoi(e)) < 1 ? 1u : uint32_t(atoi(e));
-            const size_t budget = (227u * 1024u) / per_sm - 1024u;               // per CTA, incl. the 1 KB the driver reserves
-            uint32_t t = 0;
-            while (t < 13 && slab_smem_bytes(stages, 2u << t, k) <= budget) ++t;
-            if (const char *e = getenv("B2_TALLY_TILE_LOG2")) t = uint32_t(atoi(e));
-            const size_t smem_slab = slab_smem_bytes(stages, 1u << t, k);
-            uint64_t want = rows ? (rows + 2ull * kSlabStageRows - 1) / (2ull * kSlabStageRows)
-                                 : (uint64_t(n_images) + 1023) / 1024;
-            const uint64_t cap_ctas = uint64_t(per_sm) * uint64_t(sm_count());
-            if (want > cap_ctas) want = cap_ctas;
-            if (want < 1) want = 1;
-            auto launch = [&](auto kern) -> int {
-                B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(kern), smem_slab));
-                kern<<<uint32_t(want), kSlabThreads, smem_slab, st>>>(d_image_idx, d_class_idx, d_active, rows,
-                                                                     int32_t(image_base), n_images, k, t, d_counts, partials);
-                B2_LAUNCH_CHECK("tally_slab_kernel");
-                return B2_OK;
-            };
-            if (stages == 2) {
-                if (k <= 32) return launch(tally_slab_kernel<1, 2>);
-                if (k <= 64) return launch(tally_slab_kernel<2, 2>);
-                if (k <= 128) return launch(tally_slab_kernel<4, 2>);
-                return launch(tally_slab_kernel<8, 2>);
-            }
-            if (k <= 32) return launch(tally_slab_kernel<1, 3>);
-            if (k <= 64) return launch(tally_slab_kernel<2, 3>);
-            if (k <= 128) return launch(tally_slab_kernel<4, 3>);
-            return launch(tally_slab_kernel<8, 3>);
-        }
-        if (path == 2) {                                     // shared-memory-atomic tile kernel (comparison only)
-            B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_sorted_kernel), smem));
-            uint64_t want = (rows + 4ull * kBlockRows - 1) / (4ull * kBlockRows);
-            const uint64_t by_images = (uint64_t(n_images) + tile_images - 1) / tile_images;
-            if (want < by_images) want = by_images;
-            const uint64_t cap = 2ull * uint64_t(sm_count());
-            const uint32_t grid = uint32_t(want < 1 ? 1 : (want > cap ? cap : want));
-            tally_sorted_kernel<<<grid, kTallyThreads, smem, st>>>(d_image_idx, d_class_idx, d_active, rows,
-                                                                   int32_t(image_base), n_images, k, tile_images,
-                                                                   d_counts, partials);
-            B2_LAUNCH_CHECK("tally_sorted_kernel");
-            return B2_OK;
-        }
-        // one warp per ~4096 rows (or per 64 images when there are no rows), at most one resident wave
-        const uint64_t warps_per_cta = kWarpKernelThreads / 32;
-        uint64_t want_warps = (rows + 4095) / 4096;
-        const uint64_t by_images = (uint64_t(n_images) + 63) / 64;
-        if (rows == 0 && want_warps < by_images) want_warps = by_images;
-        if (want_warps < 1) want_warps = 1;
-        const uint64_t cap = 4ull * uint64_t(sm_count()) * warps_per_cta;   // 4 CTAs of 8 warps per SM (48 KB each): one wave
-        if (want_warps > cap) want_warps = cap;
-        if (rows > 0 && want_warps > rows / kGroupRows) want_warps = rows / kGroupRows ? rows / kGroupRows : 1;
-        const uint64_t nw = want_warps;                       // distinct, 128-row aligned nominal starts
-        const uint32_t grid = uint32_t((nw + warps_per_cta - 1) / warps_per_cta);
-        B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(tally_warp_kernel), kWarpKernelSmem));
-        tally_warp_kernel<<<grid, kWarpKernelThreads, kWarpKernelSmem, st>>>(d_image_idx, d_class_idx, d_active, rows,
-                                                                            int32_t(image_base), n_images, k, nw,
-                                                                            d_counts, partials);
-        B2_LAUNCH_CHECK("tally_warp_kernel");
-        return B2_OK;
+        if (k <= 32) return launch(tally_slab_kernel<1, 3>);
+        if (k <= 64) return launch(tally_slab_kernel<2, 3>);
+        if (k <= 128) return launch(tally_slab_kernel<4, 3>);
+        return launch(tally_slab_kernel<8, 3>);
     }
     B2_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, size_t(n_images) * k * 4, st));
     if (rows) {

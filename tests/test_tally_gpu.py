@@ -25,15 +25,16 @@ def _compare(img, cls, act, n_images, k, sorted_by_image, image_base=0):
 
 @pytest.mark.parametrize("n_images,k,n_raters", [(1000, 50, 10), (1, 1, 1), (37, 3, 5), (5000, 50, 100),
                                                  (300, 255, 7), (100_000, 50, 20), (2049, 17, 33), (40, 50, 3000)])
-@pytest.mark.parametrize("mode", ["sorted", "sorted-image-kernel", "sorted-warp-kernel", "sorted-tile-kernel",
-                                  "sorted-slab-kernel", "scatter"])
+@pytest.mark.parametrize("mode", ["sorted", "sorted-2-stage-ring", "sorted-tiny-window", "scatter"])
 def test_synthetic_rows(n_images, k, n_raters, mode, monkeypatch):
-    """Every sorted-mode kernel (auto choice, thread-per-image, MATCH.ANY warp, shared-atomic tile) and the
-    any-order kernel against the oracle, bit-exact."""
-    path = {"sorted-image-kernel": "0", "sorted-warp-kernel": "1", "sorted-tile-kernel": "2",
-            "sorted-slab-kernel": "3"}.get(mode)
-    if path is not None:
-        monkeypatch.setenv("B2_TALLY_PATH", path)
+    """The sorted-mode (slab) kernel in its default geometry, with a 2-deep ring at three CTAs per SM and with
+    a 4-image counter window (every stage re-scanned window by window), and the any-order kernel, against the
+    oracle, bit-exact."""
+    if mode == "sorted-2-stage-ring":
+        monkeypatch.setenv("B2_TALLY_STAGES", "2")
+        monkeypatch.setenv("B2_TALLY_CTAS", "3")
+    if mode == "sorted-tiny-window":
+        monkeypatch.setenv("B2_TALLY_TILE_LOG2", "2")
     img, cls, act = synth_label_rows(n_images, k, n_raters, shuffled=(mode == "scatter"))
     res, p = _compare(img, cls, act, n_images, k, sorted_by_image=(mode != "scatter"))
     if n_raters > 1 and p["R"] > 0:
@@ -41,10 +42,13 @@ def test_synthetic_rows(n_images, k, n_raters, mode, monkeypatch):
         assert res.kappa(n_images, n_raters) == fleiss_kappa(p["class_totals"], p["S2"], p["R"], n_images, n_raters)
 
 
-@pytest.fixture(params=["auto", "image", "warp", "tile", "slab"])
+@pytest.fixture(params=["default", "2-stage-ring", "tiny-window"])
 def tally_path(request, monkeypatch):
-    if request.param != "auto":
-        monkeypatch.setenv("B2_TALLY_PATH", {"image": "0", "warp": "1", "tile": "2", "slab": "3"}[request.param])
+    if request.param == "2-stage-ring":
+        monkeypatch.setenv("B2_TALLY_STAGES", "2")
+        monkeypatch.setenv("B2_TALLY_CTAS", "3")
+    if request.param == "tiny-window":
+        monkeypatch.setenv("B2_TALLY_TILE_LOG2", "2")
     return request.param
 
 
@@ -102,7 +106,8 @@ def test_edge_cases_sorted(tally_path):
 @pytest.mark.parametrize("seed", range(12))
 def test_random_shapes_all_sorted_kernels(seed, monkeypatch):
     """Randomised row distributions (empty images, one-row images, very long images, gaps, odd k, non-zero
-    image_base, ragged table ends) through every sorted-mode kernel, twice each: bit-exact and repeatable."""
+    image_base, ragged table ends) through the sorted-mode kernel in three geometries, twice each: bit-exact
+    and repeatable."""
     rng = np.random.default_rng(1000 + seed)
     n_images = int(rng.integers(1, 6000))
     k = int(rng.choice([1, 2, 7, 31, 32, 33, 50, 64, 65, 128, 129, 200, 256]))
@@ -120,14 +125,14 @@ def test_random_shapes_all_sorted_kernels(seed, monkeypatch):
     cls = rng.integers(0, k, size=img.size).astype(np.uint8)
     act = (rng.random(img.size) < 0.9).astype(np.uint8)
     want = label_tally(img.astype(np.int64) - base, cls, act, n_images, k)
-    for path in (None, "0", "1", "2", "3"):
-        if path is None:
-            monkeypatch.delenv("B2_TALLY_PATH", raising=False)
-        else:
-            monkeypatch.setenv("B2_TALLY_PATH", path)
+    for env in ({}, {"B2_TALLY_STAGES": "2", "B2_TALLY_CTAS": "3"}, {"B2_TALLY_TILE_LOG2": "1"}):
+        for name in ("B2_TALLY_STAGES", "B2_TALLY_CTAS", "B2_TALLY_TILE_LOG2"):
+            monkeypatch.delenv(name, raising=False)
+        for name, v in env.items():
+            monkeypatch.setenv(name, v)
         for _ in range(2):
             res = labels.label_tally(img, cls, act, n_images, k, sorted_by_image=True, image_base=base)
-            assert np.array_equal(res.counts, want), (seed, path, n_images, k, kind)
+            assert np.array_equal(res.counts, want), (seed, env, n_images, k, kind)
             assert res.R == int(act.sum())
 
 
