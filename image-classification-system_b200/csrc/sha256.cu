@@ -10,14 +10,10 @@
 // kernel is bound by the INT32 ALU pipe (~1400 LOP3/SHF/IADD3 per 64-byte block), not by
 // HBM — see DESIGN.md "sha256_lanes".
 //
-// Two load paths:
-//   sha256_lanes_kernel   — each lane streams its own message with 128-bit loads (four per
-//                           64-byte block, prefetched one block ahead).  Every 32-byte
-//                           sector fetched is fully used, so DRAM traffic = message bytes.
-//   sha256_staged_kernel  — the warp's 32 messages are staged through shared memory by the
-//                           bulk-copy engine (cp.async.bulk, one 1-D copy per lane per
-//                           stage, mbarrier-tracked), double buffered, and each lane
-//                           compresses from its own padded shared-memory row.
+// sha256_lanes_kernel: each lane streams its own message with 128-bit loads (four per 64-byte block,
+// prefetched one block ahead).  Every 32-byte sector fetched is fully used, so DRAM traffic = message bytes
+// (ncu: 19.87 GB read for 19.86 GB of messages).  A variant that staged the warp's 32 messages through shared
+// memory with per-lane cp.async.bulk copies measured 760 GB/s against 825 and was removed.
 #include "common.cuh"
 
 #include <mutex>
@@ -55,9 +51,8 @@ struct Sha256State {
 
 // Integer add, optionally forced onto the FMA pipe.  ncu on this kernel (profiles/r1_*): the ALU
 // pipe (SHF/LOP3/IADD3/PRMT) is 87 % busy and the FMA pipe 4 %.  Every rotate and boolean has to
-// stay on the ALU pipe, an add does not.  V = 0 leaves the choice to ptxas (mostly IADD3), V = 1
-// turns every add into an IMAD — an experiment that LOST (see sha_variant_override) and is kept
-// selectable for batches with several warps per sub-partition.
+// stay on the ALU pipe, an add does not.  V = 0 leaves the choice to ptxas (mostly IADD3); V = 2 sends
+// the two-input adds to the FMA pipe as IMADs (see sha_variant_override for when that pays).
 template <int V>
 __device__ __forceinline__ uint32_t addp(uint32_t a, uint32_t b, uint32_t one) {
     if (V == 0) return a + b;
@@ -75,7 +70,6 @@ __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b, uint32_t one) {
 }
 template <int V>
 __device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c, uint32_t one) {
-    if (V == 1) return addp<1>(addp<1>(a, b, one), c, one);
     if (V == 2) {
         uint32_t d;                                   // kept as one IADD3: ptxas must not re-associate it with the IMADs
         asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -215,111 +209,6 @@ sha256_lanes_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict
     sha256_store_digest(s, digests + 32ull * msg);
 }
 
-// ----------------------------------------------------------------------------------------
-// Path 2: warp-cooperative staging through shared memory with the bulk-copy (TMA) engine.
-// One warp per CTA-slice owns 32 messages.  Per stage, lane l asks the copy engine for the
-// next kSeg bytes of ITS message into row l of the stage buffer (row pitch kSeg + 16 so that
-// the 32 rows start in different bank groups: LDS.128 by all lanes is conflict-free).  All
-// 32 copies of a stage complete on one mbarrier.  Lanes whose message has fewer than kSeg
-// bytes left request only the remaining whole 16-byte units; the sub-16-byte remainder is
-// read directly from global memory in the padding step.
-// Requires 16-byte aligned message starts (the host packer guarantees it; b2_sha256_batch
-// falls back to path 1 otherwise).
-// ----------------------------------------------------------------------------------------
-constexpr int kSeg = 512;                 // bytes per lane per stage (8 SHA blocks)
-constexpr int kRowPitch = kSeg + 16;
-constexpr int kStages = 2;
-constexpr int kWarpsPerCta = 2;
-
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
-sha256_staged_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ offsets,
-                     const uint64_t *__restrict__ lengths, const uint32_t *__restrict__ order,
-                     uint32_t n, uint8_t *__restrict__ digests) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *wbuf = smem_raw + size_t(warp) * kStages * 32 * kRowPitch;
-    __shared__ __align__(8) uint64_t bars[kWarpsPerCta][kStages];
-
-    const uint32_t slot = (blockIdx.x * kWarpsPerCta + warp) * 32 + lane;
-    const bool live = slot < n;
-    const uint32_t msg = live ? (order ? order[slot] : slot) : 0;
-    const uint8_t *p = live ? data + offsets[msg] : data;
-    const uint64_t len = live ? lengths[msg] : 0;
-    const uint64_t full = len & ~uint64_t(63);          // bytes in full 64-byte blocks
-    // The copy engine needs 16-byte aligned sources; a misaligned message (never produced by
-    // the host packer) skips staging and is hashed with byte loads after the staged loop.
-    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-    const uint64_t body = aligned ? full : 0;
-
-    if (lane == 0) {
-#pragma unroll
-        for (int st = 0; st < kStages; ++st) mbar_init(&bars[warp][st], 32);
-        fence_mbar_init();
-    }
-    __syncwarp();
-
-    // number of stages this warp runs = max over lanes of ceil(body / kSeg)
-    uint64_t my_stages = (body + kSeg - 1) / kSeg;
-    uint64_t warp_stages = my_stages;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const uint64_t other = __shfl_xor_sync(0xffffffffu, warp_stages, o);
-        warp_stages = other > warp_stages ? other : warp_stages;
-    }
-
-    auto issue = [&](uint64_t stage_idx) {
-        const int buf = int(stage_idx % kStages);
-        const uint64_t off = stage_idx * kSeg;
-        uint32_t bytes = 0;
-        if (off < body) bytes = uint32_t(body - off < kSeg ? body - off : kSeg);
-        // every lane arrives once per stage; lanes with data also post their byte count
-        if (bytes) {
-            mbar_arrive_expect_tx(&bars[warp][buf], bytes);
-            bulk_g2s(wbuf + (size_t(buf) * 32 + lane) * kRowPitch, p + off, bytes, &bars[warp][buf]);
-        } else {
-            mbar_arrive(&bars[warp][buf]);
-        }
-    };
-
-    Sha256State s;
-    s.init();
-    for (uint64_t st = 0; st < kStages - 1 && st < warp_stages; ++st) issue(st);
-    for (uint64_t st = 0; st < warp_stages; ++st) {
-        if (st + kStages - 1 < warp_stages) issue(st + kStages - 1);
-        const int buf = int(st % kStages);
-        mbar_wait(&bars[warp][buf], uint32_t((st / kStages) & 1));
-        const uint64_t off = st * kSeg;
-        const uint4 *row = reinterpret_cast<const uint4 *>(wbuf + (size_t(buf) * 32 + lane) * kRowPitch);
-        const int nblk = off < body ? int((body - off < kSeg ? body - off : kSeg) >> 6) : 0;
-        for (int blk = 0; blk < nblk; ++blk) {
-            uint4 q[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) q[i] = row[4 * blk + i];
-            uint32_t w[16];
-            words_from_v4(w, q);
-            sha256_compress(s, w);
-        }
-        __syncwarp();                      // all lanes done with `buf` before it is refilled
-    }
-    if (live) {
-        if (!aligned) {
-            for (uint64_t off = 0; off < full; off += 64) {
-                const uint8_t *b = p + off;
-                uint32_t w[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    w[j] = (uint32_t(b[4 * j]) << 24) | (uint32_t(b[4 * j + 1]) << 16) |
-                           (uint32_t(b[4 * j + 2]) << 8) | uint32_t(b[4 * j + 3]);
-                sha256_compress(s, w);
-            }
-        }
-        const uint8_t *tail = p + full;
-        sha256_finish(s, [&](uint32_t i) -> uint32_t { return tail[i]; },
-                      static_cast<uint32_t>(len & 63), len);
-        sha256_store_digest(s, digests + 32ull * msg);
-    }
-}
-
 __global__ void digest_hex_kernel(const uint8_t *__restrict__ digests, uint32_t n, char *__restrict__ hex) {
     // one thread per digest byte-pair word: thread t handles 4 digest bytes -> 8 hex chars
     const uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
@@ -344,20 +233,14 @@ __global__ void digest_hex_kernel(const uint8_t *__restrict__ digests, uint32_t 
 
 }  // namespace b2
 
-// Path selection: 0 = auto, 1 = force lanes, 2 = force staged (B2_SHA_PATH, read per call;
-// used by the benchmarks to compare the two kernels).
-static int sha_path_override() {
-    const char *e = getenv("B2_SHA_PATH");
-    return e ? atoi(e) : 0;
-}
-
-// B2_SHA_VARIANT: 0 = adds left to ptxas (default), 1 = adds forced onto the FMA pipe.  Measured on
-// B200 with one warp per SM sub-partition (all that 1080p images leave room for in HBM): variant 0
-// 825 GB/s, variant 1 560 GB/s — a lone warp issues one instruction every ~2 cycles whatever the
-// pipe, so what counts is the instruction count (IADD3 adds three operands, IMAD two).
+// B2_SHA_VARIANT: unset = auto, 0 = adds left to ptxas (IADD3), 2 = two-input adds forced onto the FMA pipe.
+// Measured on B200 (GB/s, 256 KiB messages; 1 / 2 / 4 warps per SM sub-partition): variant 0 819 / 850 / 861,
+// variant 2 794 / 884 / 899, and a variant with EVERY add as IMAD 734 / 852 / 870.  A lone warp issues one
+// instruction every ~2 cycles whatever the pipe, so with one warp per sub-partition (all that 1080p images
+// leave room for in HBM) only the instruction count matters; from two warps up the IMADs pay.
 static int sha_variant_override() {
     const char *e = getenv("B2_SHA_VARIANT");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : -1;
 }
 
 extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,
@@ -367,23 +250,6 @@ extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,
     if (n == 0) return B2_OK;
     B2_REQUIRE(d_data && d_offsets && d_lengths && d_digests, "b2_sha256_batch: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int path = sha_path_override();
-    if (path == 2) {
-        // staged path needs 16-byte aligned message starts; the caller asserts that by forcing it
-        B2_REQUIRE((reinterpret_cast<uintptr_t>(d_data) & 15) == 0, "staged path: d_data not 16-byte aligned");
-        const size_t smem = size_t(kWarpsPerCta) * kStages * 32 * kRowPitch;
-        static bool attr_set = false;
-        if (!attr_set) {
-            B2_CUDA_CHECK(cudaFuncSetAttribute(sha256_staged_kernel,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            attr_set = true;
-        }
-        const uint32_t warps = (n + 31) / 32;
-        const uint32_t grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
-        sha256_staged_kernel<<<grid, 32 * kWarpsPerCta, smem, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests);
-        B2_LAUNCH_CHECK("sha256_staged_kernel");
-        return B2_OK;
-    }
     // Spread warps over SM sub-partitions: small batches use one warp per CTA so the block
     // scheduler places consecutive warps on different SMs.
     const uint32_t warps = (n + 31) / 32;
@@ -397,14 +263,12 @@ extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,
     cudaGetDevice(&cur_dev);
     std::call_once(carve_once[cur_dev & 63], [] {
         cudaFuncSetAttribute(sha256_lanes_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(sha256_lanes_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(sha256_lanes_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     });
-    const int variant = sha_variant_override();
+    int variant = sha_variant_override();
+    if (variant < 0) variant = warps > uint32_t(sm_count()) * 4u ? 2 : 0;    // more than one warp per sub-partition
     if (variant == 0)
         sha256_lanes_kernel<0><<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests, 1u);
-    else if (variant == 1)
-        sha256_lanes_kernel<1><<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests, 1u);
     else
         sha256_lanes_kernel<2><<<grid, block, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests, 1u);
     B2_LAUNCH_CHECK("sha256_lanes_kernel");

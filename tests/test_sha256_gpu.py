@@ -15,9 +15,11 @@ from oracle import sha256_hex, synth_image
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["lanes", "staged"])
+@pytest.fixture(params=["iadd3", "imad"])
 def sha_path(request, monkeypatch):
-    monkeypatch.setenv("B2_SHA_PATH", {"lanes": "1", "staged": "2"}[request.param])
+    """Both code variants of the compression function: adds as ptxas schedules them (what one warp per
+    sub-partition gets) and two-input adds on the FMA pipe (what larger batches get)."""
+    monkeypatch.setenv("B2_SHA_VARIANT", {"iadd3": "0", "imad": "2"}[request.param])
     return request.param
 
 
