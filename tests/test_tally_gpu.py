@@ -25,7 +25,7 @@ def _compare(img, cls, act, n_images, k, sorted_by_image, image_base=0):
 
 @pytest.mark.parametrize("n_images,k,n_raters", [(1000, 50, 10), (1, 1, 1), (37, 3, 5), (5000, 50, 100),
                                                  (300, 255, 7), (100_000, 50, 20), (2049, 17, 33), (40, 50, 3000)])
-@pytest.mark.parametrize("mode", ["sorted", "sorted-2-stage-ring", "sorted-tiny-window", "scatter"])
+@pytest.mark.parametrize("mode", ["sorted", "sorted-2-stage-ring", "sorted-tiny-window", "sorted-aggregated-inc", "scatter"])
 def test_synthetic_rows(n_images, k, n_raters, mode, monkeypatch):
     """The sorted-mode (slab) kernel in its default geometry, with a 2-deep ring at three CTAs per SM and with
     a 4-image counter window (every stage re-scanned window by window), and the any-order kernel, against the
@@ -35,6 +35,8 @@ def test_synthetic_rows(n_images, k, n_raters, mode, monkeypatch):
         monkeypatch.setenv("B2_TALLY_CTAS", "3")
     if mode == "sorted-tiny-window":
         monkeypatch.setenv("B2_TALLY_TILE_LOG2", "2")
+    if mode == "sorted-aggregated-inc":                       # the ATOMS.POPC.INC variant (automatic for long images)
+        monkeypatch.setenv("B2_TALLY_INC", "1")
     img, cls, act = synth_label_rows(n_images, k, n_raters, shuffled=(mode == "scatter"))
     res, p = _compare(img, cls, act, n_images, k, sorted_by_image=(mode != "scatter"))
     if n_raters > 1 and p["R"] > 0:
@@ -125,8 +127,9 @@ def test_random_shapes_all_sorted_kernels(seed, monkeypatch):
     cls = rng.integers(0, k, size=img.size).astype(np.uint8)
     act = (rng.random(img.size) < 0.9).astype(np.uint8)
     want = label_tally(img.astype(np.int64) - base, cls, act, n_images, k)
-    for env in ({}, {"B2_TALLY_STAGES": "2", "B2_TALLY_CTAS": "3"}, {"B2_TALLY_TILE_LOG2": "1"}):
-        for name in ("B2_TALLY_STAGES", "B2_TALLY_CTAS", "B2_TALLY_TILE_LOG2"):
+    for env in ({}, {"B2_TALLY_STAGES": "2", "B2_TALLY_CTAS": "3"}, {"B2_TALLY_TILE_LOG2": "1"}, {"B2_TALLY_INC": "1"},
+                {"B2_TALLY_INC": "0"}):
+        for name in ("B2_TALLY_STAGES", "B2_TALLY_CTAS", "B2_TALLY_TILE_LOG2", "B2_TALLY_INC"):
             monkeypatch.delenv(name, raising=False)
         for name, v in env.items():
             monkeypatch.setenv(name, v)

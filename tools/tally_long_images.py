@@ -30,14 +30,20 @@ for per in (100, 132, 300, 1000, 10_000, 1_000_000):
         counts = torch.empty((N, k), dtype=torch.int32, device=dev)
         part = torch.empty(k + 7, dtype=torch.int64, device=dev)
         fn = lambda: engine.label_tally_device(img, cls, act, N, k, 0, True, counts, part)  # noqa: E731
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
+        line, ref = [], None
+        for inc in ("0", "1"):                    # plain ATOMS.ADD of 0/1 vs predicated ATOMS.POPC.INC
+            os.environ["B2_TALLY_INC"] = inc
             fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        ok = int(part[k + 1].item()) == int(act.sum().item())
-        print(f"rows/image {per:>8}  class skew {skew:.1f}: {ms:.3f} ms  {(6 * rows + 4 * N * k) / ms / 1e6:.0f} GB/s  R ok={ok}")
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            ok = int(part[k + 1].item()) == int(act.sum().item())
+            same = True if ref is None else bool(torch.equal(ref, counts))
+            ref = counts.clone()
+            line.append(f"inc={inc}: {ms:.3f} ms {(6 * rows + 4 * N * k) / ms / 1e6:5.0f} GB/s ok={ok and same}")
+        print(f"rows/image {per:>8}  class skew {skew:.1f}:  " + "   ".join(line))
