@@ -427,7 +427,7 @@ def run_graft(args):
     scatter_ok = bool(torch.equal(l_part[:LABEL_K + 5].cpu(), torch.from_numpy(local[:LABEL_K + 5])))
     del s_img, s_cls, s_act
     # labels e2e: rows in pinned host memory -> device -> tally -> partials back on the host
-    e_rows = 20_000_000
+    e_rows = rows                                             # the whole config-4 table of this GPU: 600 MB of host memory
     h_img, h_cls, h_act = (l_img[:e_rows].cpu().pin_memory(), l_cls[:e_rows].cpu().pin_memory(),
                            l_act[:e_rows].cpu().pin_memory())
 
