@@ -17,14 +17,66 @@
 //   b2_host_alloc/free   page-locked host memory (what makes the copies asynchronous and full speed).
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstring>
 #include <mutex>
 #include <new>
+#include <numeric>
 #include <vector>
 
 namespace b2 {
 
 constexpr int kHashStreams = 8;
 constexpr int kResizeStreams = 2;
+
+// Page-locked staging buffers for the variable-size host calls, recycled between calls (cudaHostAlloc costs
+// milliseconds).  A buffer is owned by one call at a time; the list only grows to what concurrent callers need.
+struct PinnedPool {
+    struct Buf { void *p; size_t bytes; };
+    std::mutex mu;
+    std::vector<Buf> free_list;
+    void *acquire(size_t bytes, size_t *got) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            int best = -1;
+            for (int i = 0; i < int(free_list.size()); ++i)
+                if (free_list[i].bytes >= bytes && (best < 0 || free_list[i].bytes < free_list[best].bytes)) best = i;
+            if (best >= 0) {
+                Buf b = free_list[best];
+                free_list.erase(free_list.begin() + best);
+                *got = b.bytes;
+                return b.p;
+            }
+        }
+        size_t want = (bytes + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);        // whole MiB
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        *got = want;
+        return p;
+    }
+    void release(void *p, size_t bytes) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (free_list.size() >= 8) {                         // keep the largest few
+            auto it = std::min_element(free_list.begin(), free_list.end(),
+                                       [](const Buf &a, const Buf &b) { return a.bytes < b.bytes; });
+            if (it->bytes < bytes) { cudaFreeHost(it->p); *it = Buf{p, bytes}; } else cudaFreeHost(p);
+            return;
+        }
+        free_list.push_back(Buf{p, bytes});
+    }
+};
+static PinnedPool g_pinned;
+
+static void keep_pool_memory(int device) {                   // freed device blocks stay in the pool between calls
+    static std::once_flag once[64];
+    std::call_once(once[device & 63], [&] {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    });
+}
 
 }  // namespace b2
 
@@ -288,16 +340,7 @@ extern "C" int b2_label_tally_host(int device, const int32_t *h_image_idx, const
         }                                                                                               \
     } while (0)
     B2_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    {
-        static std::once_flag pool_once[64];                 // keep freed blocks in the pool between calls
-        std::call_once(pool_once[device & 63], [&] {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-                uint64_t keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-        });
-    }
+    keep_pool_memory(device);
     const size_t r = size_t(rows ? rows : 1);
     B2_TRY(cudaMallocAsync(&d_img, r * 4, st));
     B2_TRY(cudaMallocAsync(&d_cls, r, st));
@@ -317,4 +360,133 @@ extern "C" int b2_label_tally_host(int device, const int32_t *h_image_idx, const
 #undef B2_TRY
     cleanup();
     return b2_label_tally_status(h_partials, k, rows);
+}
+
+// ---- variable-size messages in host memory (the service's 50-file batches) -------------------------------
+// h_msgs[i] points to h_lens[i] bytes anywhere in host memory (e.g. the buffers of Python bytes objects).  The
+// messages are packed, 16-byte aligned, into one recycled page-locked buffer, copied in one transfer, hashed in
+// order of decreasing length (a warp's 32 lanes finish together) and the digests (and optionally their lowercase
+// hex form, the String(64) primary key) are read back.  Blocking.
+extern "C" int b2_sha256_host(int device, const uint8_t *const *h_msgs, const uint64_t *h_lens, uint32_t n,
+                              uint8_t *h_digests, char *h_hex) {
+    using namespace b2;
+    if (n == 0) return B2_OK;
+    B2_REQUIRE(h_msgs && h_lens && h_digests, "b2_sha256_host: null pointer");
+    int rc = b2_init(device);
+    if (rc != B2_OK) return rc;
+    keep_pool_memory(device);
+    std::vector<uint64_t> meta(size_t(n) * 2);               // offsets then lengths
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        B2_REQUIRE(h_lens[i] == 0 || h_msgs[i] != nullptr, "b2_sha256_host: message %u is NULL", i);
+        meta[i] = total;
+        meta[n + i] = h_lens[i];
+        total += (h_lens[i] + 15) & ~uint64_t(15);
+    }
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h_lens[a] > h_lens[b]; });
+    const size_t data_bytes = size_t(total ? total : 16);
+    const size_t meta_off = (data_bytes + 255) & ~size_t(255);
+    const size_t order_off = meta_off + size_t(n) * 16;
+    const size_t in_bytes = order_off + size_t(n) * 4;       // staged input: data | offsets | lengths | order
+    const size_t out_bytes = size_t(n) * 96;                 // digests | hex
+    size_t got = 0;
+    uint8_t *stage = static_cast<uint8_t *>(g_pinned.acquire(in_bytes + out_bytes, &got));
+    if (!stage) return fail(B2_ERR_CUDA, "b2_sha256_host: cannot allocate %zu bytes of page-locked memory", in_bytes + out_bytes);
+    for (uint32_t i = 0; i < n; ++i)
+        if (h_lens[i]) memcpy(stage + meta[i], h_msgs[i], size_t(h_lens[i]));
+    memcpy(stage + meta_off, meta.data(), size_t(n) * 16);
+    memcpy(stage + order_off, order.data(), size_t(n) * 4);
+    cudaStream_t st = nullptr;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    auto cleanup = [&]() {
+        if (st) {
+            if (d_in) cudaFreeAsync(d_in, st);
+            if (d_out) cudaFreeAsync(d_out, st);
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+        g_pinned.release(stage, got);
+    };
+#define B2_TRY(expr)                                                                                    \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            cleanup();                                                                                  \
+            return fail(B2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                               \
+    } while (0)
+    B2_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    B2_TRY(cudaMallocAsync(&d_in, in_bytes, st));
+    B2_TRY(cudaMallocAsync(&d_out, out_bytes, st));
+    B2_TRY(cudaMemcpyAsync(d_in, stage, in_bytes, cudaMemcpyHostToDevice, st));
+    rc = b2_sha256_batch(d_in, reinterpret_cast<const uint64_t *>(d_in + meta_off),
+                         reinterpret_cast<const uint64_t *>(d_in + meta_off) + n,
+                         reinterpret_cast<const uint32_t *>(d_in + order_off), n, d_out, st);
+    if (rc == B2_OK && h_hex) rc = b2_digest_hex(d_out, n, reinterpret_cast<char *>(d_out + size_t(n) * 32), st);
+    if (rc != B2_OK) { cleanup(); return rc; }
+    uint8_t *h_out = stage + in_bytes;
+    B2_TRY(cudaMemcpyAsync(h_out, d_out, h_hex ? out_bytes : size_t(n) * 32, cudaMemcpyDeviceToHost, st));
+    B2_TRY(cudaStreamSynchronize(st));
+#undef B2_TRY
+    memcpy(h_digests, h_out, size_t(n) * 32);
+    if (h_hex) memcpy(h_hex, h_out + size_t(n) * 32, size_t(n) * 64);
+    cleanup();
+    return B2_OK;
+}
+
+// The dedupe decision of b2_dedupe for digests held in host memory.  Blocking.
+extern "C" int b2_dedupe_host(int device, const uint8_t *h_digests, const uint8_t *h_valid, uint32_t n,
+                              const uint8_t *h_existing_sorted, uint64_t m, uint8_t *h_is_new,
+                              int32_t *h_first_index, int32_t *h_last_index, uint32_t *h_counts) {
+    using namespace b2;
+    B2_REQUIRE(h_counts != nullptr, "b2_dedupe_host: null counts");
+    h_counts[0] = h_counts[1] = h_counts[2] = 0;
+    if (n == 0) return B2_OK;
+    B2_REQUIRE(h_digests && h_is_new, "b2_dedupe_host: null pointer");
+    B2_REQUIRE(m == 0 || h_existing_sorted != nullptr, "b2_dedupe_host: null existing table");
+    int rc = b2_init(device);
+    if (rc != B2_OK) return rc;
+    keep_pool_memory(device);
+    const uint64_t ws_bytes = b2_dedupe_workspace_bytes(n);
+    // one device block: digests | existing | valid | is_new | first | last | counts | workspace (256-byte aligned parts)
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o_dig = 0, o_ex = up(size_t(n) * 32), o_val = o_ex + up(size_t(m) * 32), o_new = o_val + up(n),
+                 o_first = o_new + up(n), o_last = o_first + up(size_t(n) * 4), o_cnt = o_last + up(size_t(n) * 4),
+                 o_ws = o_cnt + 256, bytes = o_ws + up(size_t(ws_bytes ? ws_bytes : 8));
+    cudaStream_t st = nullptr;
+    uint8_t *d = nullptr;
+    auto cleanup = [&]() {
+        if (st) {
+            if (d) cudaFreeAsync(d, st);
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    };
+#define B2_TRY(expr)                                                                                    \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            cleanup();                                                                                  \
+            return fail(B2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                               \
+    } while (0)
+    B2_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    B2_TRY(cudaMallocAsync(&d, bytes, st));
+    B2_TRY(cudaMemcpyAsync(d + o_dig, h_digests, size_t(n) * 32, cudaMemcpyHostToDevice, st));
+    if (m) B2_TRY(cudaMemcpyAsync(d + o_ex, h_existing_sorted, size_t(m) * 32, cudaMemcpyHostToDevice, st));
+    if (h_valid) B2_TRY(cudaMemcpyAsync(d + o_val, h_valid, n, cudaMemcpyHostToDevice, st));
+    rc = b2_dedupe(d + o_dig, h_valid ? d + o_val : nullptr, nullptr, n, m ? d + o_ex : nullptr, m, d + o_new,
+                   reinterpret_cast<int32_t *>(d + o_first), reinterpret_cast<int32_t *>(d + o_last),
+                   reinterpret_cast<uint32_t *>(d + o_cnt), d + o_ws, ws_bytes, st);
+    if (rc != B2_OK) { cleanup(); return rc; }
+    B2_TRY(cudaMemcpyAsync(h_is_new, d + o_new, n, cudaMemcpyDeviceToHost, st));
+    if (h_first_index) B2_TRY(cudaMemcpyAsync(h_first_index, d + o_first, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+    if (h_last_index) B2_TRY(cudaMemcpyAsync(h_last_index, d + o_last, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+    B2_TRY(cudaMemcpyAsync(h_counts, d + o_cnt, 12, cudaMemcpyDeviceToHost, st));
+    B2_TRY(cudaStreamSynchronize(st));
+#undef B2_TRY
+    cleanup();
+    return B2_OK;
 }

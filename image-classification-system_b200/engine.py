@@ -165,16 +165,50 @@ def hex_strings(hex_dev: torch.Tensor) -> List[str]:
     return [flat[i:i + 64] for i in range(0, len(flat), 64)]
 
 
+def sha256_host(datas: Sequence[bytes], device: Optional[int] = None, want_hex: bool = True):
+    """``b2_sha256_host``: byte strings in host memory -> (digests uint8[n,32], hex strings or None).  The
+    library packs the messages into its own page-locked staging buffer; nothing here touches a tensor."""
+    dev = init(device)
+    datas = [d if isinstance(d, bytes) else bytes(d) for d in datas]
+    n = len(datas)
+    digests = np.empty((n, 32), dtype=np.uint8)
+    if n == 0:
+        return digests, ([] if want_hex else None)
+    ptrs = (C.c_char_p * n)(*datas)                     # the bytes objects' own buffers, no copy
+    lens = (C.c_uint64 * n)(*[len(d) for d in datas])
+    hexbuf = C.create_string_buffer(n * 64) if want_hex else None
+    check(lib.b2_sha256_host(dev, C.cast(ptrs, C.c_void_p), C.cast(lens, C.c_void_p), n, digests.ctypes.data,
+                             C.cast(hexbuf, C.c_void_p) if want_hex else None))
+    if not want_hex:
+        return digests, None
+    flat = hexbuf.raw.decode("ascii")
+    return digests, [flat[i:i + 64] for i in range(0, n * 64, 64)]
+
+
+def dedupe_host(digests: np.ndarray, valid: Optional[np.ndarray] = None, existing_sorted: Optional[np.ndarray] = None,
+                device: Optional[int] = None):
+    """``b2_dedupe_host``: digests uint8[n,32] (+ validity flags, + the sorted table of stored digests) in host
+    memory -> ``(is_new u8[n], first_index i32[n], last_index i32[n], (processed, created, updated))``."""
+    dev = init(device)
+    d = np.ascontiguousarray(digests, dtype=np.uint8).reshape(-1, 32)
+    n = d.shape[0]
+    v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+    ex = None if existing_sorted is None or existing_sorted.size == 0 else np.ascontiguousarray(existing_sorted, dtype=np.uint8)
+    is_new = np.zeros(n, dtype=np.uint8)
+    first = np.full(n, -1, dtype=np.int32)
+    last = np.full(n, -1, dtype=np.int32)
+    counts = np.zeros(4, dtype=np.uint32)
+    check(lib.b2_dedupe_host(dev, d.ctypes.data if n else None, v.ctypes.data if v is not None else None, n,
+                             ex.ctypes.data if ex is not None else None, 0 if ex is None else ex.size // 32,
+                             is_new.ctypes.data, first.ctypes.data, last.ctypes.data, counts.ctypes.data))
+    return is_new, first, last, (int(counts[0]), int(counts[1]), int(counts[2]))
+
+
 def hash_batch(datas: Sequence[bytes], device: Optional[int] = None) -> List[str]:
     """Batched form of ``hashlib.sha256(data).hexdigest()`` (reference: webdav_sync.py:59,
-    activity_api_sync.py:798, routes/images.py:62) for a list of host byte strings."""
-    if len(datas) == 0:
-        init(device)
-        return []
-    packed = PackedMessages(datas)
-    d_data, d_off, d_len, d_order = packed.to_device(device)
-    digests = sha256_device(d_data, d_off, d_len, d_order)
-    return hex_strings(digest_hex_device(digests))
+    activity_api_sync.py:798, routes/images.py:62) for a list of host byte strings: one ``b2_sha256_host``
+    call with the byte strings' own buffers."""
+    return sha256_host(datas, device)[1]
 
 
 # --------------------------------------------------------------------------- a4: dedupe

@@ -10,7 +10,6 @@ from dataclasses import dataclass, field
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
-import torch
 
 from . import engine
 
@@ -40,14 +39,11 @@ def hash_and_dedupe(datas: Sequence[Optional[bytes]], existing_hashes=None,
     callable ``f(list_of_hex) -> iterable of those present`` (one ``IN`` query).
     """
     n = len(datas)
-    dev = torch.device("cuda", engine.init(device))
+    engine.init(device)
     if n == 0:
         return DedupeDecision([], [], [], [], {"processed": 0, "created": 0, "updated": 0})
     valid_np = np.fromiter((d is not None for d in datas), dtype=np.uint8, count=n)
-    packed = engine.PackedMessages([d if d is not None else b"" for d in datas])
-    d_data, d_off, d_len, d_order = packed.to_device(dev.index)
-    digests = engine.sha256_device(d_data, d_off, d_len, d_order)
-    hex_all = engine.hex_strings(engine.digest_hex_device(digests))
+    digests, hex_all = engine.sha256_host([d if d is not None else b"" for d in datas], device)
     hashes: List[Optional[str]] = [h if v else None for h, v in zip(hex_all, valid_np)]
 
     present = [h for h in hashes if h is not None]
@@ -56,18 +52,14 @@ def hash_and_dedupe(datas: Sequence[Optional[bytes]], existing_hashes=None,
     else:
         existing = set(existing_hashes) if existing_hashes is not None else set()
     existing &= set(present)              # only the keys this batch can hit matter
-    d_existing = None
-    if existing:
-        d_existing = torch.from_numpy(engine.sort_digests(_hex_to_digests(sorted(existing)))).to(dev)
-    d_valid = torch.from_numpy(valid_np).to(dev)
-    is_new, first, last, counts = engine.dedupe_device(digests, valid=d_valid, existing_sorted=d_existing)
-    c = counts.cpu().numpy()
+    table = engine.sort_digests(_hex_to_digests(sorted(existing))) if existing else None
+    is_new, first, last, c = engine.dedupe_host(digests, valid_np, table, device)
     return DedupeDecision(
         hashes=hashes,
-        is_new=[bool(x) for x in is_new.cpu().numpy()],
-        first_index=[int(x) for x in first.cpu().numpy()],
-        last_index=[int(x) for x in last.cpu().numpy()],
-        stats={"processed": int(c[0]), "created": int(c[1]), "updated": int(c[2])},
+        is_new=[bool(x) for x in is_new],
+        first_index=[int(x) for x in first],
+        last_index=[int(x) for x in last],
+        stats={"processed": c[0], "created": c[1], "updated": c[2]},
     )
 
 

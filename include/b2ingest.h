@@ -194,6 +194,15 @@ int b2_ingest_stream_submit(b2_ingest_stream *s, const uint8_t *h_images, uint32
                             uint8_t *h_thumbs, float *h_previews);
 int b2_ingest_stream_wait(b2_ingest_stream *s, uint64_t *h2d_bytes, uint64_t *d2h_bytes,
                           uint32_t *kernel_launches);
+/* SHA-256 of n byte strings anywhere in host memory (h_msgs[i] -> h_lens[i] bytes: e.g. the buffers of the
+ * downloaded files, webdav_sync.py:441-445): packed into a recycled page-locked buffer, one copy, one kernel,
+ * digests (n*32) and optionally their lowercase hex form (n*64, no terminator) back.  Blocking. */
+int b2_sha256_host(int device, const uint8_t *const *h_msgs, const uint64_t *h_lens, uint32_t n,
+                   uint8_t *h_digests, char *h_hex);
+/* b2_dedupe for digests, validity flags (NULL = all valid) and the sorted table in host memory.  Blocking. */
+int b2_dedupe_host(int device, const uint8_t *h_digests, const uint8_t *h_valid, uint32_t n,
+                   const uint8_t *h_existing_sorted, uint64_t m, uint8_t *h_is_new,
+                   int32_t *h_first_index, int32_t *h_last_index, uint32_t *h_counts /*3*/);
 /* Label rows in host memory -> h_partials (int64[k + B2_PARTIALS_EXTRA]) and, if not NULL, the count
  * matrix h_counts (int32[n_images * k]).  Blocking; returns the verdict of b2_label_tally_status. */
 int b2_label_tally_host(int device, const int32_t *h_image_idx, const uint8_t *h_class_idx,

@@ -96,3 +96,29 @@ def test_full_size_property_duplicates_and_checksum():
         assert bytes(dig[i]) == hashlib.sha256(data[i].cpu().numpy().tobytes()).digest()
     hexes = engine.hex_strings(engine.digest_hex_device(torch.from_numpy(dig).cuda()))
     assert hexes[50] == hashlib.sha256(data[50].cpu().numpy().tobytes()).hexdigest()
+
+
+def test_host_entry_points_match_device_path_and_oracle():
+    """b2_sha256_host / b2_dedupe_host (host pointers only) against hashlib and the sequential oracle, incl.
+    empty messages, non-bytes buffers, skipped entries and a table of stored digests."""
+    import hashlib
+    from oracle import dedupe_batch
+    rng = np.random.default_rng(11)
+    msgs = [bytes(rng.integers(0, 256, size=int(n), dtype=np.uint8)) for n in
+            [0, 1, 55, 56, 63, 64, 65, 119, 120, 4096, 100_003, 0, 1 << 20]]
+    msgs += [msgs[4], bytearray(msgs[9]), memoryview(msgs[10])]
+    digests, hexes = engine.sha256_host(msgs)
+    want = [hashlib.sha256(bytes(m)).hexdigest() for m in msgs]
+    assert hexes == want and [bytes(d).hex() for d in digests] == want
+    d2, none = engine.sha256_host(msgs, want_hex=False)
+    assert none is None and np.array_equal(d2, digests)
+    assert engine.sha256_host([]) [1] == []
+    valid = np.ones(len(msgs), dtype=np.uint8)
+    valid[[2, 7]] = 0
+    stored = {want[1], want[12], hashlib.sha256(b"elsewhere").hexdigest()}
+    table = engine.sort_digests(np.frombuffer(bytes.fromhex("".join(sorted(stored))), dtype=np.uint8).reshape(-1, 32))
+    is_new, first, last, counts = engine.dedupe_host(digests, valid, table)
+    hashes = [h if v else None for h, v in zip(want, valid)]
+    o_new, o_first, o_stats = dedupe_batch(hashes, stored)
+    assert [bool(x) for x in is_new] == o_new and first.tolist() == o_first
+    assert dict(zip(("processed", "created", "updated"), counts)) == o_stats
