@@ -95,3 +95,37 @@ def test_lookup_sorted():
     out = engine.lookup_sorted_device(torch.from_numpy(q).cuda(), torch.from_numpy(s).cuda()).cpu().tolist()
     assert out == [0, 499, 250, 3, -1, -1, -1, -1]
     assert engine.lookup_sorted_device(torch.from_numpy(q).cuda(), None).cpu().tolist() == [-1] * 8
+
+
+def test_config3_scale_two_million_digests_with_existing_table():
+    """Config 3 scale after the all-gather (1 M images over 8 GPUs -> every rank resolves all of them; 2 M here):
+    random 32-byte digests, 25 % duplicates, arrival order given by a permuted global index, 100 k of the
+    distinct digests already stored.  Oracle: NumPy group-by on the digest bytes."""
+    rng = np.random.default_rng(77)
+    n, nu = 2_000_000, 1_500_000
+    uniq = rng.integers(0, 256, size=(nu, 32), dtype=np.uint8)
+    src = np.concatenate([np.arange(nu), rng.integers(0, nu, size=n - nu)])
+    rng.shuffle(src)
+    seq = rng.permutation(n).astype(np.int32)
+    stored_ids = rng.choice(nu, size=100_000, replace=False)
+    table = engine.sort_digests(uniq[stored_ids])
+    dig = torch.from_numpy(np.ascontiguousarray(uniq[src])).cuda()
+    is_new, first, last, counts = engine.dedupe_device(dig, seq=torch.from_numpy(seq).cuda(),
+                                                       existing_sorted=torch.from_numpy(table).cuda())
+    is_new, first, last = is_new.cpu().numpy().astype(bool), first.cpu().numpy(), last.cpu().numpy()
+    # oracle: per source id, the member with the smallest / largest seq
+    order = np.lexsort((seq, src))
+    s_sorted = src[order]
+    starts = np.r_[0, np.flatnonzero(s_sorted[1:] != s_sorted[:-1]) + 1]
+    ends = np.r_[starts[1:], n]
+    first_of = np.empty(nu, dtype=np.int64)
+    last_of = np.empty(nu, dtype=np.int64)
+    present = s_sorted[starts]
+    first_of[present] = order[starts]
+    last_of[present] = order[ends - 1]
+    assert np.array_equal(first, first_of[src]) and np.array_equal(last, last_of[src])
+    stored = np.zeros(nu, dtype=bool)
+    stored[stored_ids] = True
+    want_new = (first_of[src] == np.arange(n)) & ~stored[src]
+    assert np.array_equal(is_new, want_new)
+    assert counts.cpu().tolist() == [n, int(want_new.sum()), n - int(want_new.sum())]
