@@ -71,6 +71,7 @@ SIGNATURES = {
     "b2_fleiss_workspace_bytes": (C.c_uint64, [C.c_uint32]),
     "b2_fleiss_partials": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint64, _vp]),
     "b2_distinct_images_per_annotator": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp, _vp]),
+    "b2_encode_label_rows": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "b2_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),
     "b2_host_free": (C.c_int, [_vp]),
     "b2_ingest_stream_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int,

@@ -149,6 +149,80 @@ lookup_sorted_kernel(const uint8_t *__restrict__ digests, uint32_t n, const uint
     found[i] = m ? find_sorted(existing, m, load_digest(digests, i)) : -1;
 }
 
+// ---- dictionary-encode rows of table `classificacoes` -----------------------------
+// id_img arrives as the 64 lowercase hex characters of the content hash (String(64) foreign key,
+// app/db/models.py:229), id_opc as a 16-byte UUID (:231), ativo as a byte (:233).  The image dictionary is the
+// sorted digest table of b2_dedupe (image index = position), the option dictionary the environment's sorted
+// option UUIDs (class index = position).  A thread per row: decode the hex key (rejecting anything that is
+// not [0-9a-f]), binary-search both dictionaries (the image table of 1 M keys = 32 MB stays in L2).
+__device__ __forceinline__ bool hex_word(uint32_t c4lo, uint32_t c4hi, uint32_t &out) {
+    // eight ASCII hex characters (c4lo = chars 0..3, c4hi = chars 4..7) -> four bytes in memory order
+    uint32_t v = 0;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t c = ((i < 4 ? c4lo : c4hi) >> (8 * (i & 3))) & 0xffu;
+        const bool digit = c - 0x30u <= 9u, alpha = c - 0x61u <= 5u;
+        ok &= digit | alpha;
+        const uint32_t nib = digit ? c - 0x30u : c - 0x57u;
+        v |= (nib & 0xfu) << (8 * (i >> 1) + ((i & 1) ? 0 : 4));       // first character of a pair = high nibble
+    }
+    out = v;
+    return ok;
+}
+
+__device__ __forceinline__ int cmp16(const uint4 &a, const uint4 &b) {
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t x = __byte_perm(aw[j], 0, 0x0123), y = __byte_perm(bw[j], 0, 0x0123);
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+encode_label_rows_kernel(const char *__restrict__ img_hex, const uint8_t *__restrict__ opc_uuid,
+                         const uint8_t *__restrict__ ativo, uint64_t rows, const uint8_t *__restrict__ image_keys,
+                         uint64_t n_images, const uint8_t *__restrict__ option_keys, uint32_t k,
+                         int32_t *__restrict__ image_idx, uint8_t *__restrict__ class_idx, uint8_t *__restrict__ active,
+                         unsigned long long *__restrict__ unknown) {
+    uint32_t bad_img = 0, bad_opc = 0;
+    for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < rows; r += uint64_t(gridDim.x) * blockDim.x) {
+        const uint4 *hx = reinterpret_cast<const uint4 *>(img_hex + 64 * r);
+        const uint4 h0 = __ldg(hx), h1 = __ldg(hx + 1), h2 = __ldg(hx + 2), h3 = __ldg(hx + 3);
+        Digest key;
+        bool ok = hex_word(h0.x, h0.y, key.lo.x);
+        ok &= hex_word(h0.z, h0.w, key.lo.y);
+        ok &= hex_word(h1.x, h1.y, key.lo.z);
+        ok &= hex_word(h1.z, h1.w, key.lo.w);
+        ok &= hex_word(h2.x, h2.y, key.hi.x);
+        ok &= hex_word(h2.z, h2.w, key.hi.y);
+        ok &= hex_word(h3.x, h3.y, key.hi.z);
+        ok &= hex_word(h3.z, h3.w, key.hi.w);
+        const int64_t pos = ok && n_images ? find_sorted(image_keys, n_images, key) : -1;
+        image_idx[r] = int32_t(pos);
+        bad_img += pos < 0;
+        const uint4 u = __ldg(reinterpret_cast<const uint4 *>(opc_uuid + 16 * r));
+        uint32_t lo = 0, hi = k, cls = 0xffu;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const int c = cmp16(__ldg(reinterpret_cast<const uint4 *>(option_keys + 16 * size_t(mid))), u);
+            if (c == 0) { cls = mid; break; }
+            if (c < 0) lo = mid + 1; else hi = mid;
+        }
+        class_idx[r] = uint8_t(cls);
+        bad_opc += cls == 0xffu;
+        active[r] = ativo[r] ? 1 : 0;
+    }
+    bad_img = __reduce_add_sync(0xffffffffu, bad_img);
+    bad_opc = __reduce_add_sync(0xffffffffu, bad_opc);
+    if ((threadIdx.x & 31) == 0) {
+        if (bad_img) atomicAdd(&unknown[0], (unsigned long long)bad_img);
+        if (bad_opc) atomicAdd(&unknown[1], (unsigned long long)bad_opc);
+    }
+}
+
 static uint32_t table_capacity(uint32_t n) {
     uint64_t cap = 64;
     while (cap < 2ull * n) cap <<= 1;
@@ -203,5 +277,32 @@ extern "C" int b2_lookup_sorted(const uint8_t *d_digests, uint32_t n, const uint
                "b2_lookup_sorted: d_existing must be non-null and 16-byte aligned when m > 0");
     lookup_sorted_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_digests, n, d_existing, m, d_found_index);
     B2_LAUNCH_CHECK("lookup_sorted_kernel");
+    return B2_OK;
+}
+
+extern "C" int b2_encode_label_rows(const char *d_img_hex, const uint8_t *d_opc_uuid, const uint8_t *d_ativo,
+                                    uint64_t rows, const uint8_t *d_image_keys, uint64_t n_images,
+                                    const uint8_t *d_option_keys, uint32_t k, int32_t *d_image_idx,
+                                    uint8_t *d_class_idx, uint8_t *d_active, uint64_t *d_unknown, void *stream) {
+    using namespace b2;
+    B2_REQUIRE(d_unknown != nullptr, "b2_encode_label_rows: null d_unknown");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B2_CUDA_CHECK(cudaMemsetAsync(d_unknown, 0, 16, st));
+    if (rows == 0) return B2_OK;
+    B2_REQUIRE(d_img_hex && d_opc_uuid && d_ativo && d_image_idx && d_class_idx && d_active, "b2_encode_label_rows: null pointer");
+    B2_REQUIRE(k <= 255, "b2_encode_label_rows: at most 255 options (class 255 marks an unknown option)");
+    B2_REQUIRE(n_images < 0x7fffffffull, "b2_encode_label_rows: image dictionary too large for int32 indices");
+    B2_REQUIRE(n_images == 0 || d_image_keys, "b2_encode_label_rows: null image dictionary");
+    B2_REQUIRE(k == 0 || d_option_keys, "b2_encode_label_rows: null option dictionary");
+    B2_REQUIRE(((reinterpret_cast<uintptr_t>(d_img_hex) | reinterpret_cast<uintptr_t>(d_opc_uuid) |
+                 reinterpret_cast<uintptr_t>(d_image_keys) | reinterpret_cast<uintptr_t>(d_option_keys)) & 15) == 0,
+               "b2_encode_label_rows: keys and dictionaries must be 16-byte aligned");
+    uint64_t grid = (rows + 255) / 256;
+    const uint64_t cap = 32ull * uint64_t(sm_count());
+    if (grid > cap) grid = cap;
+    encode_label_rows_kernel<<<unsigned(grid), 256, 0, st>>>(d_img_hex, d_opc_uuid, d_ativo, rows, d_image_keys, n_images,
+                                                            d_option_keys, k, d_image_idx, d_class_idx, d_active,
+                                                            reinterpret_cast<unsigned long long *>(d_unknown));
+    B2_LAUNCH_CHECK("encode_label_rows_kernel");
     return B2_OK;
 }

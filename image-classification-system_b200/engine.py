@@ -391,6 +391,31 @@ def partials_dict(partials_host: np.ndarray, k: int) -> Dict[str, object]:
     return out
 
 
+def encode_label_rows_device(img_hex: torch.Tensor, opc_uuid: torch.Tensor, ativo: torch.Tensor,
+                             image_keys_sorted: torch.Tensor, option_keys_sorted: torch.Tensor):
+    """``b2_encode_label_rows``: rows of table ``classificacoes`` as raw keys on the device — ``img_hex`` uint8[R,64]
+    (the char64 id_img), ``opc_uuid`` uint8[R,16], ``ativo`` uint8[R] — against the sorted image-digest table
+    uint8[N,32] and the sorted option UUIDs uint8[k,16].  Returns ``(image_idx int32[R], class_idx uint8[R],
+    active uint8[R], unknown int64[2])``; image -1 / class 255 mark keys missing from a dictionary."""
+    _need_cuda(img_hex, opc_uuid, ativo, image_keys_sorted, option_keys_sorted)
+    dev = img_hex.device
+    init(dev.index)
+    rows = ativo.numel()
+    assert img_hex.dtype == torch.uint8 and img_hex.numel() == rows * 64
+    assert opc_uuid.dtype == torch.uint8 and opc_uuid.numel() == rows * 16 and ativo.dtype == torch.uint8
+    n_images = image_keys_sorted.numel() // 32
+    k = option_keys_sorted.numel() // 16
+    image_idx = torch.empty(rows, dtype=torch.int32, device=dev)
+    class_idx = torch.empty(rows, dtype=torch.uint8, device=dev)
+    active = torch.empty(rows, dtype=torch.uint8, device=dev)
+    unknown = torch.empty(2, dtype=torch.int64, device=dev)
+    check(lib.b2_encode_label_rows(_ptr(img_hex), _ptr(opc_uuid), _ptr(ativo), rows,
+                                   _ptr(image_keys_sorted) if n_images else None, n_images,
+                                   _ptr(option_keys_sorted) if k else None, k,
+                                   _ptr(image_idx), _ptr(class_idx), _ptr(active), _ptr(unknown), _stream()))
+    return image_idx, class_idx, active, unknown
+
+
 def fleiss_partials_device(counts: torch.Tensor, want_sum_pi: bool = False):
     """Partials (and optionally the float64 sum of per-image agreements P_i) from a count matrix."""
     _need_cuda(counts)

@@ -142,3 +142,48 @@ class LabelEncoder:
         act = np.fromiter((1 if r["ativo"] is True else 0 for r in rows), dtype=np.uint8, count=n)
         order = np.argsort(img, kind="stable")
         return img[order], cls[order], act[order]
+
+
+class DeviceLabelEncoder:
+    """Bulk form of :class:`LabelEncoder`: the dictionaries live on the device
+    as sorted key tables — stored image digests (the table ``b2_dedupe`` already uses) and the environment's option
+    UUIDs — and whole row sets are encoded by ``b2_encode_label_rows``.  Image index = position of the hash in
+    ``sorted(image_hashes)``, class index = position of the option among the UUIDs sorted by their bytes."""
+
+    def __init__(self, image_hashes: Sequence[str], option_ids: Sequence[str], device: Optional[int] = None):
+        import uuid
+        self.dev = torch.device("cuda", engine.init(device))
+        self.image_hashes = sorted(image_hashes)
+        keys = np.frombuffer(bytes.fromhex("".join(self.image_hashes)), dtype=np.uint8).reshape(-1, 32) \
+            if self.image_hashes else np.zeros((0, 32), np.uint8)
+        self.option_ids = sorted((uuid.UUID(str(o)) for o in option_ids), key=lambda u: u.bytes)
+        if len(self.option_ids) > 255:
+            raise ValueError("class_idx is uint8 and 255 marks an unknown option: at most 255 options per environment")
+        opts = np.frombuffer(b"".join(u.bytes for u in self.option_ids), dtype=np.uint8).reshape(-1, 16) \
+            if self.option_ids else np.zeros((0, 16), np.uint8)
+        self.d_image_keys = torch.from_numpy(np.array(keys, copy=True)).to(self.dev)       # hex order = byte order
+        self.d_option_keys = torch.from_numpy(np.array(opts, copy=True)).to(self.dev)
+
+    def encode_columns(self, img_hex: torch.Tensor, opc_uuid: torch.Tensor, ativo: torch.Tensor, sort: bool = True):
+        """Raw key columns (device or host tensors: uint8[R,64], uint8[R,16], uint8[R]) -> device SoA arrays
+        ``(image_idx, class_idx, active, unknown)``; with ``sort`` the rows come back ordered by image index
+        (stable), ready for the sorted-mode tally."""
+        cols = [c.to(self.dev, non_blocking=True).contiguous() for c in (img_hex, opc_uuid, ativo)]
+        img, cls, act, unknown = engine.encode_label_rows_device(cols[0], cols[1], cols[2], self.d_image_keys,
+                                                                 self.d_option_keys)
+        if sort:
+            order = torch.sort(img, stable=True).indices
+            img, cls, act = img[order].contiguous(), cls[order].contiguous(), act[order].contiguous()
+        return img, cls, act, unknown
+
+    def encode(self, rows: Sequence[Dict], sort: bool = True):
+        """Row dicts with id_img (64-char hex), id_opc (UUID or its string), ativo -> the same as
+        :meth:`encode_columns`."""
+        import uuid
+        n = len(rows)
+        hexs = np.frombuffer("".join(str(r["id_img"]).ljust(64)[:64] for r in rows).encode("latin-1", "replace"),
+                             dtype=np.uint8).reshape(n, 64) if n else np.zeros((0, 64), np.uint8)
+        opcs = np.frombuffer(b"".join(uuid.UUID(str(r["id_opc"])).bytes for r in rows), dtype=np.uint8).reshape(n, 16) \
+            if n else np.zeros((0, 16), np.uint8)
+        act = np.fromiter((1 if r["ativo"] is True else 0 for r in rows), dtype=np.uint8, count=n)
+        return self.encode_columns(torch.from_numpy(hexs.copy()), torch.from_numpy(opcs.copy()), torch.from_numpy(act), sort)

@@ -163,6 +163,20 @@ int b2_distinct_images_per_annotator(const int32_t *d_annotator_idx, const int32
                                      const uint8_t *d_active, uint64_t rows, uint32_t n_annotators,
                                      uint32_t *d_distinct, void *stream);
 
+/* ---- next row (f2 i): dictionary-encode rows of `classificacoes` for the tally ---------------------
+ * Row r: id_img = 64 lowercase hex characters at d_img_hex + 64 r (String(64) foreign key,
+ * app/db/models.py:229), id_opc = 16-byte UUID at d_opc_uuid + 16 r (:231), ativo = d_ativo[r] (:233).
+ * Dictionaries: d_image_keys = the n_images stored digests sorted in memcmp order (the table b2_dedupe
+ * takes as `existing`; image index = position), d_option_keys = the k <= 255 option UUIDs of the environment
+ * sorted in memcmp order (class index = position).  Outputs the SoA arrays b2_label_tally reads:
+ * d_image_idx[r] (-1 = unknown image or a key that is not 64 characters of [0-9a-f]), d_class_idx[r]
+ * (255 = unknown option), d_active[r] = ativo != 0; d_unknown[2] = rows with an unknown image / option.
+ * Keys and dictionaries must be 16-byte aligned. */
+int b2_encode_label_rows(const char *d_img_hex, const uint8_t *d_opc_uuid, const uint8_t *d_ativo,
+                         uint64_t rows, const uint8_t *d_image_keys, uint64_t n_images,
+                         const uint8_t *d_option_keys, uint32_t k, int32_t *d_image_idx,
+                         uint8_t *d_class_idx, uint8_t *d_active, uint64_t *d_unknown, void *stream);
+
 /* ---- host-buffer entry points: the end-to-end form of the path --------------------------------
  * What the reference holds when the path starts is bytes in HOST memory: downloaded files
  * (app/services/webdav_sync.py:441, the 50-image batch loop :273-283) and rows fetched from table

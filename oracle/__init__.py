@@ -55,6 +55,7 @@ from .labels import (  # noqa: F401
     distinct_image_count,
     history_grouping,
     classification_delta,
+    encode_label_rows,
 )
 from .synth import (  # noqa: F401
     synth_image,

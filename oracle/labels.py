@@ -149,3 +149,24 @@ def classification_delta(
     tinha = len(ativas) > 0
     inc = (total_novas > 0 or (bool(reativar) and not tinha)) and not tinha
     return inativar, criar, reativar, total_novas, inc
+
+
+def encode_label_rows(rows: Sequence[Dict], image_hashes: Sequence[str], option_ids: Sequence[str]):
+    """Dictionary-encode rows of table ``classificacoes`` (app/db/models.py:224-241) for the tally:
+    ``id_img`` (char64 foreign key, :229) -> position of the hash in ``sorted(image_hashes)`` (-1 = not a stored
+    image), ``id_opc`` (UUID, :231) -> position in the option UUIDs sorted by their 16 bytes (255 = not an option
+    of the environment), ``ativo`` (:233, compared ``== True`` as classificacao_crud.py:314 does) -> 0/1.
+    Graft-defined (the reference never builds these arrays): parity unpinned by the reference."""
+    import uuid
+    img_pos = {h: i for i, h in enumerate(sorted(image_hashes))}
+    opt_sorted = sorted(uuid.UUID(str(o)).bytes for o in option_ids)
+    opt_pos = {b: i for i, b in enumerate(opt_sorted)}
+    n = len(rows)
+    img = np.full(n, -1, dtype=np.int32)
+    cls = np.full(n, 255, dtype=np.uint8)
+    act = np.zeros(n, dtype=np.uint8)
+    for r, row in enumerate(rows):
+        img[r] = img_pos.get(row["id_img"], -1)
+        cls[r] = opt_pos.get(uuid.UUID(str(row["id_opc"])).bytes, 255)
+        act[r] = 1 if row["ativo"] is True else 0
+    return img, cls, act
