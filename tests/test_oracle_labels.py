@@ -78,3 +78,20 @@ def test_tally_matches_naive_loop():
     assert np.array_equal(counts, naive)
     p = fleiss_partials(counts)
     assert p["R"] == int(act.sum()) and p["S2"] == int((naive.astype(np.int64) ** 2).sum())
+
+
+def test_encode_label_rows_on_reference_fixture_rows(ref_labels):
+    """The dictionary encoder of the oracle against the product's host encoder on the reference's own fixture
+    rows (with sorted dictionaries both define the same dense indices), plus unknown keys."""
+    from ics_b200 import labels
+    from oracle import encode_label_rows
+    rows = ref_labels["classificacoes"]
+    hashes = sorted({r["id_img"] for r in rows})
+    options = sorted({r["id_opc"] for r in rows})
+    img, cls, act = encode_label_rows(rows, hashes, options)
+    order = np.argsort(img, kind="stable")
+    h_img, h_cls, h_act = labels.LabelEncoder(hashes, options).encode(rows)
+    assert np.array_equal(img[order], h_img) and np.array_equal(cls[order], h_cls) and np.array_equal(act[order], h_act)
+    img2, cls2, _ = encode_label_rows(rows, hashes[1:], options[1:])
+    assert (img2 == -1).sum() == sum(r["id_img"] == hashes[0] for r in rows)
+    assert (cls2 == 255).sum() == sum(r["id_opc"] == options[0] for r in rows)
