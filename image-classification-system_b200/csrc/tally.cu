@@ -750,17 +750,32 @@ __global__ void __launch_bounds__(256)
 distinct_images_kernel(const int32_t *__restrict__ annotator_idx, const int32_t *__restrict__ image_idx,
                        const uint8_t *__restrict__ active, uint64_t rows, uint32_t n_annotators,
                        uint32_t *__restrict__ distinct) {
-    for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < rows; r += uint64_t(gridDim.x) * blockDim.x) {
-        if (!active[r]) continue;
-        const int32_t a = annotator_idx[r], img = image_idx[r];
-        if (a < 0 || uint32_t(a) >= n_annotators) continue;
-        // walk back over the rows of the same (annotator, image) run looking for an earlier active one
-        bool first = true;
-        for (uint64_t q = r; q-- > 0;) {
-            if (annotator_idx[q] != a || image_idx[q] != img) break;
-            if (active[q]) { first = false; break; }
+    // A warp takes 32 consecutive rows per step.  Rows are sorted by (annotator, image), so a warp sees one or two
+    // annotators: lanes with the same annotator are grouped with MATCH.ANY and the group's first lane adds the
+    // number of "first active row of its (annotator, image) run" flags in one atomic — 32x fewer atomics than one
+    // per row, and no two lanes of a warp instruction on the same address.
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
+    const uint64_t n_warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t base = warp * 32; base < rows; base += n_warps * 32) {
+        const uint64_t r = base + lane;
+        bool first = false;
+        int32_t a = -1;
+        if (r < rows) {
+            a = annotator_idx[r];
+            if (active[r] && a >= 0 && uint32_t(a) < n_annotators) {
+                const int32_t img = image_idx[r];
+                first = true;                                  // unless an earlier active row of the same run exists
+                for (uint64_t q = r; q-- > 0;) {
+                    if (annotator_idx[q] != a || image_idx[q] != img) break;
+                    if (active[q]) { first = false; break; }
+                }
+            }
         }
-        if (first) atomicAdd(&distinct[a], 1u);
+        const uint32_t flags = __ballot_sync(0xffffffffu, first);
+        const uint32_t same = __match_any_sync(0xffffffffu, a);
+        const uint32_t mine = flags & same;
+        if (first && (mine & ((1u << lane) - 1u)) == 0) atomicAdd(&distinct[a], uint32_t(__popc(mine)));
     }
 }
 }  // namespace b2
