@@ -81,6 +81,8 @@ SIGNATURES = {
     "b2_ingest_stream_wait": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "b2_sha256_host": (C.c_int, [C.c_int, _vp, _vp, C.c_uint32, _vp, _vp]),
     "b2_dedupe_host": (C.c_int, [C.c_int, _vp, _vp, C.c_uint32, _vp, C.c_uint64, _vp, _vp, _vp, _vp]),
+    "b2_thumbnails_host": (C.c_int, [C.c_int, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp,
+                                     C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "b2_label_tally_host": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                       _vp, _vp]),
 }

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
-from ... import engine
+from ... import hostapi
 
 
 class NoFilesError(ValueError):
@@ -21,7 +21,7 @@ def buscar_imagens_por_hash(files: Sequence[Tuple[Optional[str], bytes]], db, de
     if not files:
         raise NoFilesError("Nenhuma imagem foi enviada. Envie pelo menos uma imagem.")
     is_image = [bool(ct) and ct.startswith("image/") for ct, _ in files]
-    hashes = engine.hash_batch([data for (ct, data), ok in zip(files, is_image) if ok], device)
+    hashes = hostapi.hash_batch([data for (ct, data), ok in zip(files, is_image) if ok], device)
     found = db.get_many(hashes)
     resultados: List[Dict] = []
     total = 0

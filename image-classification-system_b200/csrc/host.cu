@@ -18,10 +18,13 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <map>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <numeric>
+#include <tuple>
+#include <utility>
 #include <vector>
 
 namespace b2 {
@@ -485,6 +488,110 @@ extern "C" int b2_dedupe_host(int device, const uint8_t *h_digests, const uint8_
     if (h_first_index) B2_TRY(cudaMemcpyAsync(h_first_index, d + o_first, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
     if (h_last_index) B2_TRY(cudaMemcpyAsync(h_last_index, d + o_last, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
     B2_TRY(cudaMemcpyAsync(h_counts, d + o_cnt, 12, cudaMemcpyDeviceToHost, st));
+    B2_TRY(cudaStreamSynchronize(st));
+#undef B2_TRY
+    cleanup();
+    return B2_OK;
+}
+
+// ---- decoded images of any mix of shapes in host memory -> thumbnails / previews in host memory ----------------
+// h_rgb[i] points to image i (HWC uint8, row pitch 3*w, no padding), h_hw[2i], h_hw[2i+1] = its height and width.
+// Images are grouped by shape; each group is packed into recycled page-locked staging, copied, resized by one
+// launch with the group's cached tap plan (outputs land at the images' own positions) and read back.  Blocking.
+namespace b2 {
+struct PlanCache {
+    std::mutex mu;
+    std::map<std::tuple<int, int, int, int, int>, b2_resize_plan *> plans;   // (device, in_h, in_w, out_h, out_w)
+    int get(int device, int ih, int iw, int oh, int ow, b2_resize_plan **out) {
+        std::lock_guard<std::mutex> lock(mu);
+        auto key = std::make_tuple(device, ih, iw, oh, ow);
+        auto it = plans.find(key);
+        if (it != plans.end()) { *out = it->second; return B2_OK; }
+        b2_resize_plan *pl = nullptr;
+        const int rc = b2_resize_plan_create(ih, iw, oh, ow, &pl);
+        if (rc != B2_OK) return rc;
+        plans[key] = pl;                                     // plans live as long as the library
+        *out = pl;
+        return B2_OK;
+    }
+};
+static PlanCache g_plans;
+}  // namespace b2
+
+extern "C" int b2_thumbnails_host(int device, const uint8_t *const *h_rgb, const uint32_t *h_hw, uint32_t n,
+                                  uint32_t out_h, uint32_t out_w, uint8_t *h_thumbs, float *h_previews,
+                                  const float mean[3], const float inv_std[3]) {
+    using namespace b2;
+    if (n == 0) return B2_OK;
+    B2_REQUIRE(h_rgb && h_hw && h_thumbs, "b2_thumbnails_host: null pointer");
+    B2_REQUIRE(out_h >= 1 && out_w >= 1, "b2_thumbnails_host: empty output shape");
+    int rc = b2_init(device);
+    if (rc != B2_OK) return rc;
+    keep_pool_memory(device);
+    std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> groups;
+    for (uint32_t i = 0; i < n; ++i) {
+        B2_REQUIRE(h_rgb[i] != nullptr && h_hw[2 * i] >= 1 && h_hw[2 * i + 1] >= 1, "b2_thumbnails_host: image %u is empty", i);
+        groups[{h_hw[2 * i], h_hw[2 * i + 1]}].push_back(i);
+    }
+    const size_t out_px = size_t(out_h) * out_w * 3;
+    cudaStream_t st = nullptr;
+    uint8_t *d_thumbs = nullptr, *d_in = nullptr;
+    float *d_prev = nullptr;
+    uint8_t *stage = nullptr;
+    size_t got = 0;
+    auto cleanup = [&]() {
+        if (st) {
+            if (d_thumbs) cudaFreeAsync(d_thumbs, st);
+            if (d_prev) cudaFreeAsync(d_prev, st);
+            if (d_in) cudaFreeAsync(d_in, st);
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+        if (stage) g_pinned.release(stage, got);
+    };
+#define B2_TRY(expr)                                                                                    \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            cleanup();                                                                                  \
+            return fail(B2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                               \
+    } while (0)
+    B2_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    B2_TRY(cudaMallocAsync(&d_thumbs, size_t(n) * out_px, st));
+    if (h_previews) B2_TRY(cudaMallocAsync(&d_prev, size_t(n) * out_px * 4, st));
+    // largest group decides the staging size: images (16-byte aligned starts) | offsets | out slots
+    size_t max_bytes = 0;
+    for (auto &g : groups) {
+        const size_t L = (size_t(g.first.first) * g.first.second * 3 + 15) & ~size_t(15);
+        const size_t b = ((L * g.second.size() + 255) & ~size_t(255)) + g.second.size() * 12;
+        if (b > max_bytes) max_bytes = b;
+    }
+    stage = static_cast<uint8_t *>(g_pinned.acquire(max_bytes, &got));
+    if (!stage) { cleanup(); return fail(B2_ERR_CUDA, "b2_thumbnails_host: cannot allocate %zu bytes of page-locked memory", max_bytes); }
+    B2_TRY(cudaMallocAsync(&d_in, max_bytes, st));
+    for (auto &g : groups) {
+        const uint32_t ih = g.first.first, iw = g.first.second, m = uint32_t(g.second.size());
+        const size_t bytes = size_t(ih) * iw * 3, L = (bytes + 15) & ~size_t(15);
+        const size_t off_off = (L * m + 255) & ~size_t(255), slot_off = off_off + size_t(m) * 8;
+        b2_resize_plan *plan = nullptr;
+        rc = g_plans.get(device, int(ih), int(iw), int(out_h), int(out_w), &plan);
+        if (rc != B2_OK) { cleanup(); return rc; }
+        uint64_t *offs = reinterpret_cast<uint64_t *>(stage + off_off);
+        uint32_t *slots = reinterpret_cast<uint32_t *>(stage + slot_off);
+        for (uint32_t j = 0; j < m; ++j) {
+            memcpy(stage + L * j, h_rgb[g.second[j]], bytes);
+            offs[j] = L * j;
+            slots[j] = g.second[j];
+        }
+        B2_TRY(cudaMemcpyAsync(d_in, stage, slot_off + size_t(m) * 4, cudaMemcpyHostToDevice, st));
+        rc = b2_resize_normalize_batch(plan, d_in, reinterpret_cast<const uint64_t *>(d_in + off_off),
+                                       reinterpret_cast<const uint32_t *>(d_in + slot_off), m, d_thumbs, d_prev, mean, inv_std, st);
+        if (rc != B2_OK) { cleanup(); return rc; }
+        B2_TRY(cudaStreamSynchronize(st));                   // the staging buffer is reused by the next group
+    }
+    B2_TRY(cudaMemcpyAsync(h_thumbs, d_thumbs, size_t(n) * out_px, cudaMemcpyDeviceToHost, st));
+    if (h_previews) B2_TRY(cudaMemcpyAsync(h_previews, d_prev, size_t(n) * out_px * 4, cudaMemcpyDeviceToHost, st));
     B2_TRY(cudaStreamSynchronize(st));
 #undef B2_TRY
     cleanup();

@@ -165,50 +165,7 @@ def hex_strings(hex_dev: torch.Tensor) -> List[str]:
     return [flat[i:i + 64] for i in range(0, len(flat), 64)]
 
 
-def sha256_host(datas: Sequence[bytes], device: Optional[int] = None, want_hex: bool = True):
-    """``b2_sha256_host``: byte strings in host memory -> (digests uint8[n,32], hex strings or None).  The
-    library packs the messages into its own page-locked staging buffer; nothing here touches a tensor."""
-    dev = init(device)
-    datas = [d if isinstance(d, bytes) else bytes(d) for d in datas]
-    n = len(datas)
-    digests = np.empty((n, 32), dtype=np.uint8)
-    if n == 0:
-        return digests, ([] if want_hex else None)
-    ptrs = (C.c_char_p * n)(*datas)                     # the bytes objects' own buffers, no copy
-    lens = (C.c_uint64 * n)(*[len(d) for d in datas])
-    hexbuf = C.create_string_buffer(n * 64) if want_hex else None
-    check(lib.b2_sha256_host(dev, C.cast(ptrs, C.c_void_p), C.cast(lens, C.c_void_p), n, digests.ctypes.data,
-                             C.cast(hexbuf, C.c_void_p) if want_hex else None))
-    if not want_hex:
-        return digests, None
-    flat = hexbuf.raw.decode("ascii")
-    return digests, [flat[i:i + 64] for i in range(0, n * 64, 64)]
-
-
-def dedupe_host(digests: np.ndarray, valid: Optional[np.ndarray] = None, existing_sorted: Optional[np.ndarray] = None,
-                device: Optional[int] = None):
-    """``b2_dedupe_host``: digests uint8[n,32] (+ validity flags, + the sorted table of stored digests) in host
-    memory -> ``(is_new u8[n], first_index i32[n], last_index i32[n], (processed, created, updated))``."""
-    dev = init(device)
-    d = np.ascontiguousarray(digests, dtype=np.uint8).reshape(-1, 32)
-    n = d.shape[0]
-    v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
-    ex = None if existing_sorted is None or existing_sorted.size == 0 else np.ascontiguousarray(existing_sorted, dtype=np.uint8)
-    is_new = np.zeros(n, dtype=np.uint8)
-    first = np.full(n, -1, dtype=np.int32)
-    last = np.full(n, -1, dtype=np.int32)
-    counts = np.zeros(4, dtype=np.uint32)
-    check(lib.b2_dedupe_host(dev, d.ctypes.data if n else None, v.ctypes.data if v is not None else None, n,
-                             ex.ctypes.data if ex is not None else None, 0 if ex is None else ex.size // 32,
-                             is_new.ctypes.data, first.ctypes.data, last.ctypes.data, counts.ctypes.data))
-    return is_new, first, last, (int(counts[0]), int(counts[1]), int(counts[2]))
-
-
-def hash_batch(datas: Sequence[bytes], device: Optional[int] = None) -> List[str]:
-    """Batched form of ``hashlib.sha256(data).hexdigest()`` (reference: webdav_sync.py:59,
-    activity_api_sync.py:798, routes/images.py:62) for a list of host byte strings: one ``b2_sha256_host``
-    call with the byte strings' own buffers."""
-    return sha256_host(datas, device)[1]
+from .hostapi import dedupe_host, hash_batch, sha256_host, sort_digests  # noqa: E402,F401  (host-pointer layer)
 
 
 # --------------------------------------------------------------------------- a4: dedupe
@@ -243,17 +200,6 @@ def lookup_sorted_device(digests: torch.Tensor, existing_sorted: Optional[torch.
     out = torch.empty(n, dtype=torch.int64, device=digests.device)
     check(lib.b2_lookup_sorted(_ptr(digests), n, _ptr(existing_sorted) if m else None, m, _ptr(out), _stream()))
     return out
-
-
-def sort_digests(digests: np.ndarray) -> np.ndarray:
-    """Host helper: sort uint8[m,32] digests in memcmp order (the order b2_dedupe expects for
-    ``existing``).  Index maintenance, not on the hot path."""
-    if digests.size == 0:
-        return digests.reshape(0, 32)
-    d = np.ascontiguousarray(digests.reshape(-1, 32))
-    keys = d.view(">u8").reshape(-1, 4)
-    idx = np.lexsort((keys[:, 3], keys[:, 2], keys[:, 1], keys[:, 0]))
-    return np.ascontiguousarray(d[idx])
 
 
 # --------------------------------------------------------------------------- a12: resize
@@ -352,9 +298,6 @@ def thumbnails(images: Sequence[np.ndarray], out_h: int = 256, out_w: int = 256,
 
 
 # --------------------------------------------------------------------------- a13: tally
-PARTIAL_NAMES = ("S2", "R", "n_rated", "n_pairs_images", "pairs", "rows_seen", "unsorted_pairs")
-
-
 def label_tally_device(image_idx: torch.Tensor, class_idx: torch.Tensor, active: torch.Tensor,
                        n_images: int, k: int, image_base: int = 0, sorted_by_image: bool = True,
                        counts: Optional[torch.Tensor] = None, partials: Optional[torch.Tensor] = None):
@@ -377,18 +320,7 @@ def label_tally_device(image_idx: torch.Tensor, class_idx: torch.Tensor, active:
     return counts, partials
 
 
-def check_tally(partials_host: np.ndarray, k: int, rows: int) -> None:
-    """Raise B2Error if the tally met unsorted rows (sorted mode) or out-of-range rows."""
-    p = np.ascontiguousarray(partials_host, dtype=np.int64)
-    check(lib.b2_label_tally_status(p.ctypes.data, k, rows))
-
-
-def partials_dict(partials_host: np.ndarray, k: int) -> Dict[str, object]:
-    p = np.asarray(partials_host, dtype=np.int64)
-    out: Dict[str, object] = {"class_totals": p[:k].copy()}
-    for i, name in enumerate(PARTIAL_NAMES):
-        out[name] = int(p[k + i])
-    return out
+from .hostapi import PARTIAL_NAMES, check_tally, partials_dict  # noqa: E402,F401
 
 
 def encode_label_rows_device(img_hex: torch.Tensor, opc_uuid: torch.Tensor, ativo: torch.Tensor,

@@ -11,7 +11,7 @@ from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
 
-from . import engine
+from . import hostapi
 
 
 @dataclass
@@ -39,11 +39,11 @@ def hash_and_dedupe(datas: Sequence[Optional[bytes]], existing_hashes=None,
     callable ``f(list_of_hex) -> iterable of those present`` (one ``IN`` query).
     """
     n = len(datas)
-    engine.init(device)
+    hostapi.init(device)
     if n == 0:
         return DedupeDecision([], [], [], [], {"processed": 0, "created": 0, "updated": 0})
     valid_np = np.fromiter((d is not None for d in datas), dtype=np.uint8, count=n)
-    digests, hex_all = engine.sha256_host([d if d is not None else b"" for d in datas], device)
+    digests, hex_all = hostapi.sha256_host([d if d is not None else b"" for d in datas], device)
     hashes: List[Optional[str]] = [h if v else None for h, v in zip(hex_all, valid_np)]
 
     present = [h for h in hashes if h is not None]
@@ -52,8 +52,8 @@ def hash_and_dedupe(datas: Sequence[Optional[bytes]], existing_hashes=None,
     else:
         existing = set(existing_hashes) if existing_hashes is not None else set()
     existing &= set(present)              # only the keys this batch can hit matter
-    table = engine.sort_digests(_hex_to_digests(sorted(existing))) if existing else None
-    is_new, first, last, c = engine.dedupe_host(digests, valid_np, table, device)
+    table = hostapi.sort_digests(_hex_to_digests(sorted(existing))) if existing else None
+    is_new, first, last, c = hostapi.dedupe_host(digests, valid_np, table, device)
     return DedupeDecision(
         hashes=hashes,
         is_new=[bool(x) for x in is_new],
@@ -80,7 +80,7 @@ def ingest_batch(datas: Sequence[Optional[bytes]], decoded_rgb: Optional[Sequenc
     if decoded_rgb is not None:
         idx = [i for i, im in enumerate(decoded_rgb) if im is not None]
         if idx:
-            t, p = engine.thumbnails([decoded_rgb[i] for i in idx], out_h, out_w, want_preview, device=device)
+            t, p = hostapi.thumbnails([decoded_rgb[i] for i in idx], out_h, out_w, want_preview, device=device)
             thumbs = np.zeros((len(datas), out_h, out_w, 3), dtype=np.uint8)
             thumbs[idx] = t
             if p is not None:

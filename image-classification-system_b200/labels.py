@@ -16,9 +16,21 @@ from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
 
 import numpy as np
-import torch
 
-from . import engine
+from . import hostapi
+
+import sys
+
+
+def _engine():
+    from . import engine                  # device-pointer layer (imports PyTorch)
+    return engine
+
+
+def _is_tensor(a) -> bool:
+    """True for a PyTorch tensor — without importing PyTorch (if it is not loaded, nobody can hold one)."""
+    t = sys.modules.get("torch")
+    return t is not None and isinstance(a, t.Tensor)
 
 
 @dataclass
@@ -54,7 +66,8 @@ def fleiss_kappa_general(class_totals: Sequence[int], R: int, sum_pi: float, n_p
 
 
 def _rows_to_device(image_idx, class_idx, active, device):
-    dev = torch.device("cuda", engine.init(device))
+    import torch
+    dev = torch.device("cuda", _engine().init(device))
 
     def up(a, dt):
         if isinstance(a, torch.Tensor):
@@ -76,37 +89,21 @@ def label_tally(image_idx, class_idx, active, n_images: int, k: int, sorted_by_i
             sorted_by_image = bool(np.all(image_idx[1:] >= image_idx[:-1])) if image_idx.size else True
         else:
             sorted_by_image = True
-    if not any(isinstance(a, torch.Tensor) for a in (image_idx, class_idx, active)):
+    if not any(_is_tensor(a) for a in (image_idx, class_idx, active)):
         # host rows: one native call with host pointers (b2_label_tally_host stages, tallies, reads back, checks)
         counts, p = label_tally_host(image_idx, class_idx, active, n_images, k, sorted_by_image, image_base, device)
     else:
         d_img, d_cls, d_act = _rows_to_device(image_idx, class_idx, active, device)
-        d_counts, partials = engine.label_tally_device(d_img, d_cls, d_act, n_images, k, image_base, sorted_by_image)
+        d_counts, partials = _engine().label_tally_device(d_img, d_cls, d_act, n_images, k, image_base, sorted_by_image)
         p = partials.cpu().numpy()
-        engine.check_tally(p, k, d_img.numel())
+        hostapi.check_tally(p, k, d_img.numel())
         counts = d_counts.cpu().numpy()
-    d = engine.partials_dict(p, k)
+    d = hostapi.partials_dict(p, k)
     return TallyResult(counts=counts, class_totals=d["class_totals"], S2=d["S2"], R=d["R"],
                        n_rated=d["n_rated"], n_pairs_images=d["n_pairs_images"], pairs=d["pairs"])
 
 
-def label_tally_host(image_idx, class_idx, active, n_images: int, k: int, sorted_by_image: bool = True,
-                     image_base: int = 0, device: Optional[int] = None, want_counts: bool = True):
-    """Rows in host memory (anything ``np.asarray`` accepts) through ``b2_label_tally_host``: host pointers in,
-    ``(counts int32[n_images,k] or None, partials int64[k+7])`` out; raises ``B2Error`` for unsorted rows
-    (sorted mode) or rows out of range.  No tensor library involved."""
-    from ._lib import B2_PARTIALS_EXTRA, B2_TALLY_SORTED, check, lib
-    dev = engine.init(device)
-    img = np.ascontiguousarray(image_idx, dtype=np.int32)
-    cls = np.ascontiguousarray(class_idx, dtype=np.uint8)
-    act = np.ascontiguousarray(active, dtype=np.uint8)
-    assert img.ndim == 1 and cls.shape == img.shape and act.shape == img.shape
-    counts = np.empty((n_images, k), dtype=np.int32) if want_counts else None
-    partials = np.empty(k + B2_PARTIALS_EXTRA, dtype=np.int64)
-    check(lib.b2_label_tally_host(dev, img.ctypes.data, cls.ctypes.data, act.ctypes.data, img.size, image_base,
-                                  n_images, k, B2_TALLY_SORTED if sorted_by_image else 0,
-                                  counts.ctypes.data if counts is not None else None, partials.ctypes.data))
-    return counts, partials
+label_tally_host = hostapi.label_tally_host
 
 
 def distinct_images_per_annotator(annotator_idx, image_idx, active, n_annotators: int,
@@ -117,6 +114,8 @@ def distinct_images_per_annotator(annotator_idx, image_idx, active, n_annotators
     i = np.ascontiguousarray(image_idx, dtype=np.int32)
     act = np.ascontiguousarray(active, dtype=np.uint8)
     order = np.lexsort((i, a))
+    import torch
+    engine = _engine()
     dev = torch.device("cuda", engine.init(device))
     out = engine.distinct_images_per_annotator_device(
         torch.from_numpy(a[order]).to(dev), torch.from_numpy(i[order]).to(dev),
@@ -152,7 +151,8 @@ class DeviceLabelEncoder:
 
     def __init__(self, image_hashes: Sequence[str], option_ids: Sequence[str], device: Optional[int] = None):
         import uuid
-        self.dev = torch.device("cuda", engine.init(device))
+        import torch
+        self.dev = torch.device("cuda", _engine().init(device))
         self.image_hashes = sorted(image_hashes)
         keys = np.frombuffer(bytes.fromhex("".join(self.image_hashes)), dtype=np.uint8).reshape(-1, 32) \
             if self.image_hashes else np.zeros((0, 32), np.uint8)
@@ -164,13 +164,14 @@ class DeviceLabelEncoder:
         self.d_image_keys = torch.from_numpy(np.array(keys, copy=True)).to(self.dev)       # hex order = byte order
         self.d_option_keys = torch.from_numpy(np.array(opts, copy=True)).to(self.dev)
 
-    def encode_columns(self, img_hex: torch.Tensor, opc_uuid: torch.Tensor, ativo: torch.Tensor, sort: bool = True):
+    def encode_columns(self, img_hex, opc_uuid, ativo, sort: bool = True):
         """Raw key columns (device or host tensors: uint8[R,64], uint8[R,16], uint8[R]) -> device SoA arrays
         ``(image_idx, class_idx, active, unknown)``; with ``sort`` the rows come back ordered by image index
         (stable), ready for the sorted-mode tally."""
+        import torch
         cols = [c.to(self.dev, non_blocking=True).contiguous() for c in (img_hex, opc_uuid, ativo)]
-        img, cls, act, unknown = engine.encode_label_rows_device(cols[0], cols[1], cols[2], self.d_image_keys,
-                                                                 self.d_option_keys)
+        img, cls, act, unknown = _engine().encode_label_rows_device(cols[0], cols[1], cols[2], self.d_image_keys,
+                                                                    self.d_option_keys)
         if sort:
             order = torch.sort(img, stable=True).indices
             img, cls, act = img[order].contiguous(), cls[order].contiguous(), act[order].contiguous()
@@ -180,6 +181,7 @@ class DeviceLabelEncoder:
         """Row dicts with id_img (64-char hex), id_opc (UUID or its string), ativo -> the same as
         :meth:`encode_columns`."""
         import uuid
+        import torch
         n = len(rows)
         hexs = np.frombuffer("".join(str(r["id_img"]).ljust(64)[:64] for r in rows).encode("latin-1", "replace"),
                              dtype=np.uint8).reshape(n, 64) if n else np.zeros((0, 64), np.uint8)

@@ -9,7 +9,7 @@ import logging
 from datetime import datetime
 from typing import Callable, Dict, Optional
 
-from .. import engine
+from .. import hostapi
 from .webdav_sync import WebDAVSync, _utc_now
 
 logger = logging.getLogger(__name__)
@@ -33,7 +33,7 @@ class ActivityAPISync:
             if not self._validate_image(image_info):
                 return False
             image_data = self.client.get_file(image_info.get("path", "")).content
-            content_hash = engine.hash_batch([image_data], self.device)[0]
+            content_hash = hostapi.hash_batch([image_data], self.device)[0]
             row = self.db.get(content_hash)
             now = self._now()
 

@@ -28,7 +28,7 @@ import logging
 from datetime import datetime, timezone
 from typing import Callable, Dict, List, Optional, Tuple
 
-from .. import engine
+from .. import hostapi
 from ..ingest import hash_and_dedupe
 
 logger = logging.getLogger(__name__)
@@ -60,7 +60,7 @@ class WebDAVSync:
     # ------------------------------------------------------------------ single-item API
     def _calculate_hash_from_bytes(self, data: bytes) -> str:
         """SHA-256 of the file bytes, lowercase hex (64 chars): a 1-element device batch."""
-        return engine.hash_batch([data], self.device)[0]
+        return hostapi.hash_batch([data], self.device)[0]
 
     def _validate_image(self, file_info: Dict) -> bool:
         name = file_info.get("name", "").lower()

@@ -217,6 +217,12 @@ int b2_sha256_host(int device, const uint8_t *const *h_msgs, const uint64_t *h_l
 int b2_dedupe_host(int device, const uint8_t *h_digests, const uint8_t *h_valid, uint32_t n,
                    const uint8_t *h_existing_sorted, uint64_t m, uint8_t *h_is_new,
                    int32_t *h_first_index, int32_t *h_last_index, uint32_t *h_counts /*3*/);
+/* Decoded RGB images of any mix of shapes in host memory (h_rgb[i] -> h_hw[2i] x h_hw[2i+1] x 3 bytes, HWC) ->
+ * uint8 HWC thumbnails (n * out_h*out_w*3) and, if not NULL, float32 CHW previews in host memory.  Images are
+ * grouped by shape, one launch per group with a tap plan cached inside the library.  Blocking. */
+int b2_thumbnails_host(int device, const uint8_t *const *h_rgb, const uint32_t *h_hw, uint32_t n,
+                       uint32_t out_h, uint32_t out_w, uint8_t *h_thumbs, float *h_previews,
+                       const float mean[3], const float inv_std[3]);
 /* Label rows in host memory -> h_partials (int64[k + B2_PARTIALS_EXTRA]) and, if not NULL, the count
  * matrix h_counts (int32[n_images * k]).  Blocking; returns the verdict of b2_label_tally_status. */
 int b2_label_tally_host(int device, const int32_t *h_image_idx, const uint8_t *h_class_idx,
