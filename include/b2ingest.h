@@ -10,9 +10,12 @@
  *     frees or retains caller memory; outputs are caller-allocated.
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  All
  *     work is enqueued on it and the call returns without synchronising unless stated.
- *   - Re-entrant: no global mutable state except immutable per-shape coefficient tables
- *     owned by b2_resize_plan objects.  Several host threads may call concurrently (the
- *     reference reaches this path from up to five service threads).
+ *   - Re-entrant: the device-pointer entry points keep no global mutable state except immutable
+ *     per-shape coefficient tables owned by b2_resize_plan objects; the host-pointer entry points
+ *     (b2_*_host, b2_ingest_stream_*) share a mutex-guarded pool of page-locked staging buffers and a
+ *     cache of resize plans.  Several host threads may call concurrently (the reference reaches this
+ *     path from up to five service threads); a b2_ingest_stream belongs to
+ *     one thread at a time.
  *   - There is no CPU fallback.  Without a Blackwell GPU every compute entry point fails.
  *
  * Each entry point cites the reference interface (file:line under the reference repo) it

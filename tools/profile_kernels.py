@@ -3,7 +3,7 @@
 
     python tools/profile_kernels.py && \
     ncu --set full --clock-control none --import-source on \
-        -k regex:'sha256|resize_bands|tally_sorted' -o gpurun_out/prof python tools/profile_kernels.py
+        -k regex:'sha256_lanes|resize_bands|tally_slab' -c 6 -o gpurun_out/prof python tools/profile_kernels.py
 
 Sizes keep device memory small enough for ncu's save/restore between replay passes: the hash
 gets 18 944 messages of 1 MiB (one warp per SM sub-partition, same per-block work as 1080p
