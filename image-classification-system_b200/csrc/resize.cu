@@ -211,17 +211,17 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
     // horizontal taps of my column -> registers
     const bool col_active = tid < p.out_w;
     int xmin = 0;
-    int32_t kh[kPlanar ? 1 : KSH];
+    int32_t kh[KSH];                               // bands pass (unused, hence free, in the planar instantiations)
     // planar: coefficient limbs laid out against the 8-byte aligned window that starts at pixel xmin & ~7
-    uint32_t kl[kPlanar ? 3 : 1][kPlanar ? NW : 1];
+    uint32_t kl[3][NW];                            // planar pass
     if (col_active) xmin = p.hbounds[2 * tid];
-    if (!kPlanar) {
+    if constexpr (!kPlanar) {
 #pragma unroll
-        for (int t = 0; t < KSH; ++t) kh[kPlanar ? 0 : t] = 0;
+        for (int t = 0; t < KSH; ++t) kh[t] = 0;
         if (col_active) {
 #pragma unroll
             for (int t = 0; t < KSH; ++t)
-                if (t < p.ksize_h) kh[kPlanar ? 0 : t] = p.hcoeffs[tid * p.ksize_h + t];
+                if (t < p.ksize_h) kh[t] = p.hcoeffs[tid * p.ksize_h + t];
         }
     } else {
         const int off = xmin & 7;
@@ -236,7 +236,7 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
                 l1 |= ((k >> 8) & 0xffu) << (8 * b);
                 l2 |= ((k >> 16) & 0xffu) << (8 * b);
             }
-            kl[0][kPlanar ? j : 0] = l0; kl[kPlanar ? 1 : 0][kPlanar ? j : 0] = l1; kl[kPlanar ? 2 : 0][kPlanar ? j : 0] = l2;
+            kl[0][j] = l0; kl[1][j] = l1; kl[2][j] = l2;
         }
     }
     __syncthreads();
@@ -349,7 +349,7 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
 
         const int ra = r0 + s * p.rows_per_stage;
         const int rb = min(ra + p.rows_per_stage, r1);
-        if (kPlanar) {
+        if constexpr (kPlanar) {
             // ---- de-interleave the stage in place: chunk i of the stage (16 pixels, 48 bytes) becomes 16 bytes of
             // each plane at offset 16 i; a plane holds (rb - ra) rows of in_w bytes, rows contiguous.
             const uint32_t n_chunks = uint32_t(rb - ra) * uint32_t(p.in_w >> 4);
@@ -392,9 +392,9 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
                         uint32_t s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
                         for (int j = 0; j < NW; ++j) {
-                            s0 = __dp4a(w[j], kl[0][kPlanar ? j : 0], s0);
-                            s1 = __dp4a(w[j], kl[kPlanar ? 1 : 0][kPlanar ? j : 0], s1);
-                            s2 = __dp4a(w[j], kl[kPlanar ? 2 : 0][kPlanar ? j : 0], s2);
+                            s0 = __dp4a(w[j], kl[0][j], s0);
+                            s1 = __dp4a(w[j], kl[1][j], s1);
+                            s2 = __dp4a(w[j], kl[2][j], s2);
                         }
                         out[c] = to_u8<kClip>(int32_t(uint32_t(kRound) + s0 + (s1 << 8) + (s2 << 16)));
                     }
@@ -418,9 +418,9 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
 #pragma unroll
                 for (int t = 0; t < KSH; ++t) {
                     const int q0 = 3 * t, q1 = 3 * t + 1, q2 = 3 * t + 2;
-                    acc0 += int32_t(__byte_perm(v[q0 >> 2], 0, 0x4440 | (q0 & 3))) * kh[kPlanar ? 0 : t];
-                    acc1 += int32_t(__byte_perm(v[q1 >> 2], 0, 0x4440 | (q1 & 3))) * kh[kPlanar ? 0 : t];
-                    acc2 += int32_t(__byte_perm(v[q2 >> 2], 0, 0x4440 | (q2 & 3))) * kh[kPlanar ? 0 : t];
+                    acc0 += int32_t(__byte_perm(v[q0 >> 2], 0, 0x4440 | (q0 & 3))) * kh[t];
+                    acc1 += int32_t(__byte_perm(v[q1 >> 2], 0, 0x4440 | (q1 & 3))) * kh[t];
+                    acc2 += int32_t(__byte_perm(v[q2 >> 2], 0, 0x4440 | (q2 & 3))) * kh[t];
                 }
                 tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] =
                     to_u8<kClip>(acc0) | (to_u8<kClip>(acc1) << 8) | (to_u8<kClip>(acc2) << 16);
