@@ -94,3 +94,31 @@ def test_obter_contagem_vs_reference(ref_labels):
             continue
         assert classificacao_crud.obter_contagem_classificacoes(db, case["id_con"]) == {"total": case["total"]}
     assert classificacao_crud.obter_contagem_classificacoes(db, "not-a-uuid") == {"total": 0}
+
+
+def test_agrupar_historico_vs_reference(ref_labels):
+    """a10: the grouping loop of listar_historico_usuario on the reference's own page (row dicts rebuilt from the
+    committed fixture: hash, option text, option id, image path)."""
+    from ics_b200.crud.classificacao_crud import agrupar_historico
+    h = ref_labels["history"]
+    path_of = {it["content_hash"]: it["url_img"][len("/nextcloud/images/"):].replace("%20", " ") for it in h["items"]}
+    page = [({"data_criado": i}, {"content_hash": ch, "nome_img": "n", "caminho_img": "/" + path_of[ch]},
+             {"texto": texto, "id_opc": id_opc}, None, {"id_amb": "amb", "titulo_amb": "Ambiente A"})
+            for i, (ch, texto, id_opc) in enumerate(h["joined"])]
+    got = agrupar_historico(page)
+    assert [{k: it[k] for k in ("content_hash", "ids_opcoes", "opcao_escolhida", "url_img")} for it in got] == h["items"]
+    assert all(it["id_amb"] == "amb" and "opcoes_lista" not in it for it in got)
+    assert agrupar_historico(page, id_amb="x")[0]["id_amb"] == "x" and agrupar_historico([]) == []
+
+
+def test_calcular_delta_classificacao_vs_reference(ref_labels):
+    """a11: set deltas + the progress-counter rule of criar_ou_atualizar_classificacao, replayed on the states the
+    reference went through."""
+    from ics_b200.crud.classificacao_crud import calcular_delta_classificacao
+    for d in ref_labels["delta"]:
+        inativar, criar, reativar, total_novas, delta = calcular_delta_classificacao(
+            d["before_active"], d["before_inactive"], d["wanted"])
+        assert total_novas == d["total_novas"] and delta == d["counter_delta"]
+        after_active = (set(d["before_active"]) - inativar) | criar | reativar
+        after_inactive = (set(d["before_inactive"]) - reativar) | inativar
+        assert sorted(after_active) == d["after_active"] and sorted(after_inactive) == d["after_inactive"]
