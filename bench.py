@@ -477,6 +477,17 @@ def run_graft(args):
                 d["note"] = note
             return d
 
+        def int_alu_roofline(bytes_, ms, clk):
+            # the hash's real bound: 1 290 ALU-pipe warp instructions per 64-byte block per warp (SASS count and
+            # ncu: 1 416 instructions per block, 91 % of them SHF/LOP3/IADD3/PRMT), against 0.5 ALU warp
+            # instructions per clock and SM sub-partition (16 lanes) at the SM clock sampled during the run
+            sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            achieved = bytes_ / 64.0 / 32.0 * 1290.0 / (ms / 1e3) / 1e9
+            peak = sms * 4 * 0.5 * sm_mhz * 1e6 / 1e9
+            return {"bound": "int32 ALU pipe", "achieved": achieved, "peak": peak, "unit": "G warp-instructions/s",
+                    "frac": achieved / peak, "alu_instructions_per_64B_block": 1290}
+
         cores = os.cpu_count() or 1
         cpu_n = 512 * cores                                    # ~10-15 s of work on every core
         cpu_v, cpu_dt = cpu_ingest_sample(cpu_n, cores)
@@ -493,10 +504,11 @@ def run_graft(args):
                     "host_numa_node_rank0": numa_node,
                     "matches_device_path": e2e_ok},
             "gpu_launches": ingest_launches, "step_ms_rank0": ingest_step_ms,
-            "roofline": roof(sha_bytes, ms_sha, "sha256_lanes_kernel",
+            "roofline": dict(roof(sha_bytes, ms_sha, "sha256_lanes_kernel",
                              note="dominant kernel of the ingest step (79 % of it); sha256 is bound by the INT32 ALU pipe "
                                   "(1 290 ALU instructions per 64-byte block, pipe 90 % busy under ncu), not by HBM: "
                                   "frac of HBM peak is reported for reference, the HBM-bound kernels are under `kernels`"),
+                             int_alu=int_alu_roofline(sha_bytes, ms_sha, clocks)),
             "kernels": {
                 "sha256_lanes_kernel": roof(sha_bytes, ms_sha, "sha256_lanes_kernel"),
                 "resize_bands_kernel": roof(resize_bytes, ms_resize, "resize_bands_kernel",
