@@ -35,9 +35,19 @@ class B2Error(RuntimeError):
 
 def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            f"{LIB_PATH} not found: build it with `python image-classification-system_b200/build.py` "
-            "(or __graft_entry__.build()).  There is no CPU fallback for this path.")
+        # a source-only checkout: compile the library in place if the CUDA toolchain is here (nvcc cross-compiles
+        # sm_100a without a GPU); otherwise fail loudly — there is no CPU fallback for this path
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_b2_build", os.path.join(HERE, "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        except Exception as e:  # noqa: BLE001 - whatever went wrong, the message below is what the user needs
+            raise ImportError(
+                f"{LIB_PATH} not found and could not be built ({e}): build it with "
+                "`python image-classification-system_b200/build.py` (or __graft_entry__.build()).  "
+                "There is no CPU fallback for this path.") from e
     return C.CDLL(LIB_PATH)
 
 
