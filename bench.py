@@ -491,6 +491,7 @@ def run_graft(args):
         cores = os.cpu_count() or 1
         cpu_n = 512 * cores                                    # ~10-15 s of work on every core
         cpu_v, cpu_dt = cpu_ingest_sample(cpu_n, cores)
+        cpu_1, _ = cpu_ingest_sample(48, 1)                    # the reference loop is sequential per image (webdav_sync.py:311)
         line = {
             "metric": "ingest images/s", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_ingest / args.steps,
@@ -521,7 +522,8 @@ def run_graft(args):
             },
             "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": f"{cpu_n} synthetic 1920x1080x3 images, hashlib+Pillow+NumPy oracle, "
-                                       f"{cores} threads, {cpu_dt:.1f} s"},
+                                       f"{cores} threads, {cpu_dt:.1f} s",
+                             "single_thread_images_per_s": cpu_1},
             "labels": {"value": rows_per_s, "unit": "rows/s", "rows_per_gpu_per_step": rows, "steps": label_steps,
                        "ms_per_step": ms_labels / label_steps, "gpu_launches": label_launches,
                        "roofline": roof(tally_bytes, ms_tally, "tally_slab_kernel"), "kappa": kappa, "partials_ok": bool(label_ok),
