@@ -333,17 +333,21 @@ def run_graft(args):
     ms_resize_bh = kernel_ms(lambda: plan.run(flat, offsets, thumb=thumbs, preview=previews, beside_hash=True))
     ms_dedupe = kernel_ms(lambda: engine.dedupe_device(digests))
 
-    # parity spot check against the oracle inside the bench (sampled images; not timed)
+    # sanity check of the timed outputs (sampled images; not timed) against the reference's own host libraries,
+    # called directly: hashlib.sha256(...).hexdigest() (webdav_sync.py:59) and Pillow's BILINEAR resize.  (oracle/
+    # is imported by the CPU-baseline leg only.)
     parity = None
     if rank == 0:
-        from oracle import sha256_hex, thumbnail_u8
+        import hashlib
+        from PIL import Image as PILImage
         idx = [0, n_img // 2, n_img - 1]
         ok = True
         hexes = engine.hex_strings(engine.digest_hex_device(digests[idx].contiguous()))
         for j, i in enumerate(idx):
             host = data[i].cpu().numpy()
-            ok &= hexes[j] == sha256_hex(host.tobytes())
-            ok &= bool(np.array_equal(thumbs[i].cpu().numpy(), thumbnail_u8(host.reshape(IMG_H, IMG_W, 3), OUT, OUT)))
+            ok &= hexes[j] == hashlib.sha256(host.tobytes()).hexdigest()
+            want = np.asarray(PILImage.fromarray(host.reshape(IMG_H, IMG_W, 3), "RGB").resize((OUT, OUT), PILImage.BILINEAR))
+            ok &= bool(np.array_equal(thumbs[i].cpu().numpy(), want))
         exp_created = n_unique * world if world == 1 else None
         ok &= counts_h[0] == n_img * world and (exp_created is None or counts_h[1] == exp_created)
         parity = {"sampled_images": len(idx), "ok": bool(ok), "dedupe_counts": counts_h}
