@@ -8,7 +8,7 @@
 //   b2_ingest_stream_*   fixed-shape batches of decoded RGB images in host memory
 //                        -> SHA-256 digests, dedupe decision + stats, uint8 thumbnails, float32 previews
 //                        in host memory.  One copy stream feeds the batch to the device in chunks; each chunk's
-//                        hash runs on one of eight compute streams (SHA-256 is serial per message: one lane
+//                        hash runs on one of 32 compute streams (SHA-256 is serial per message: one lane
 //                        hashes a 1080p image in ~130 ms however small the chunk, so many small hash kernels
 //                        must overlap each other and the copies), its resize on one of two more, and the
 //                        results are read back while later chunks still arrive.  submit() only enqueues;
@@ -30,7 +30,7 @@
 
 namespace b2 {
 
-constexpr int kHashStreams = 8;
+constexpr int kHashStreams = 32;             // a chunk hash runs ~130 ms (1080p) to ~520 ms (4K) whatever its size: enough streams that no chunk queues behind another
 constexpr int kResizeStreams = 2;
 
 // Page-locked staging buffers for the variable-size host calls, recycled between calls (cudaHostAlloc costs

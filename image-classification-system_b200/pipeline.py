@@ -4,7 +4,7 @@
                                          \\--> dedupe over the whole batch --D2H--> flags + stats
 
 The pipeline itself is native: ``b2_ingest_stream_*`` in ``csrc/host.cu`` (C ABI, host pointers only) owns
-the device staging buffer, the copy stream, the eight hash streams and the two resize streams.  SHA-256 is
+the device staging buffer, the copy stream, the 32 hash streams and the two resize streams.  SHA-256 is
 serial per message: one lane hashes one image at ~48 MB/s, so a 1080p image takes ~130 ms however few
 images are in flight; the batch is therefore copied in small chunks and each chunk's hash kernel runs on
 one of several streams, so many hash kernels (8 warps each) overlap each other and the remaining copies;
