@@ -24,6 +24,7 @@
 // independent device implementation.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -95,6 +96,7 @@ struct b2_resize_plan {
     int tmp_pitch;        // bytes per intermediate row (multiple of 16)
     int threads;
     int ksh_bucket;       // template bucket for horizontal taps (0 = fast path unavailable)
+    int q_bucket;         // quads pass: tap capacity (multiple of 4) covering the widest horizontal window; 0 = unavailable
     int planar;           // 1 = the planar IDP.4A horizontal pass applies (in_w % 16 == 0, stage fits the register carry)
     int vparam;           // 1 = the vertical tap table fits the kernel parameters (out_h * (2 + ksize_v) <= kVtabInts)
     size_t smem_fixed;    // ring + intermediate (+ slack); the vertical tap tables add band_rows*(2+ksize_v)*4
@@ -166,9 +168,19 @@ constexpr int kPlanarChunks = 3;                 // 16-pixel chunks a thread de-
 // limbs, recombined with two shift-adds per output; 8-byte aligned windows read with LDS.64): ~80 instructions
 // per thread and input row instead of ~140 (one PRMT + one IMAD per byte-tap), a third of them on the ALU pipe.  Needs in_w % 16 == 0 (rows are whole 48-byte chunks and start
 // 16-byte aligned) and non-negative coefficients (BILINEAR).  Same integers, same result.
-template <int KSH, bool kClip = false, bool kPlanar = false, bool kVParam = false>
+//
+// kMode 2 ("quads"): no shared-memory round trip at all.  The thread's byte-aligned window (funnel-shifted as
+// in the bands pass) is de-interleaved IN REGISTERS, four pixels = three words -> one R, one G and one B word
+// (two PRMT each), and every plane word meets three coefficient-limb words in three IDP.4A: 6 PRMT + 9 IDP.4A
+// per four taps and three channels instead of 12 PRMT + 12 IMAD.  KSH is the tap capacity, a multiple of 4
+// chosen from the widest window the plan actually has (16 for 1080p -> 256, although ksize = 17); any input
+// width and alignment; needs non-negative coefficients (BILINEAR).  Same integers, same result.
+template <int KSH, bool kClip = false, int kMode = 0, bool kVParam = false>
 __global__ void __launch_bounds__(256)
 resize_bands_kernel(const __grid_constant__ ResizeParams p) {
+    constexpr bool kPlanar = kMode == 1;
+    constexpr bool kQuads = kMode == 2;
+    constexpr int NQ = (KSH + 3) / 4;           // quads: 4-pixel groups of the window
     constexpr int NV = (3 * KSH + 3) / 4;       // byte-aligned window, in 32-bit words
     constexpr int NW = 2 * ((KSH + 7 + 7) / 8); // planar: 8-byte aligned window of one plane, in 32-bit words (LDS.64)
     extern __shared__ __align__(128) uint8_t smem[];
@@ -214,8 +226,23 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
     int32_t kh[KSH];                               // bands pass (unused, hence free, in the planar instantiations)
     // planar: coefficient limbs laid out against the 8-byte aligned window that starts at pixel xmin & ~7
     uint32_t kl[3][NW];                            // planar pass
+    uint32_t kq[3][NQ];                            // quads pass: limb i of the taps under pixels 4g .. 4g+3
     if (col_active) xmin = p.hbounds[2 * tid];
-    if constexpr (!kPlanar) {
+    if constexpr (kQuads) {
+#pragma unroll
+        for (int g = 0; g < NQ; ++g) {
+            uint32_t l0 = 0, l1 = 0, l2 = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int t = 4 * g + b;
+                const uint32_t k = (col_active && t < p.ksize_h) ? uint32_t(p.hcoeffs[tid * p.ksize_h + t]) : 0u;
+                l0 |= (k & 0xffu) << (8 * b);
+                l1 |= ((k >> 8) & 0xffu) << (8 * b);
+                l2 |= ((k >> 16) & 0xffu) << (8 * b);
+            }
+            kq[0][g] = l0; kq[1][g] = l1; kq[2][g] = l2;
+        }
+    } else if constexpr (!kPlanar) {
 #pragma unroll
         for (int t = 0; t < KSH; ++t) kh[t] = 0;
         if (col_active) {
@@ -401,6 +428,41 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
                     tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] = out[0] | (out[1] << 8) | (out[2] << 16);
                 }
             }
+        } else if constexpr (kQuads) {
+            if (col_active) {
+                uint32_t src = smem_u32(sbuf) + uint32_t(uint64_t(ra) * pitch - a0) + 3u * xmin;
+                for (int r = ra; r < rb; ++r, src += uint32_t(pitch)) {
+                    const uint32_t base = src & ~3u;
+                    const uint32_t sh = (src & 3u) * 8u;
+                    uint32_t w[3 * NQ + 1];
+#pragma unroll
+                    for (int j = 0; j < 3 * NQ + 1; ++j)
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[j]) : "r"(base + 4u * j));
+                    uint32_t s[3][3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { s[c][0] = uint32_t(kRound); s[c][1] = 0; s[c][2] = 0; }
+#pragma unroll
+                    for (int g = 0; g < NQ; ++g) {
+                        const uint32_t w0 = __funnelshift_r(w[3 * g], w[3 * g + 1], sh);
+                        const uint32_t w1 = __funnelshift_r(w[3 * g + 1], w[3 * g + 2], sh);
+                        const uint32_t w2 = __funnelshift_r(w[3 * g + 2], w[3 * g + 3], sh);
+                        uint32_t px[3];
+                        px[0] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);     // R of pixels 4g .. 4g+3
+                        px[1] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);     // G
+                        px[2] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);     // B
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            s[c][0] = __dp4a(px[c], kq[0][g], s[c][0]);
+                            s[c][1] = __dp4a(px[c], kq[1][g], s[c][1]);
+                            s[c][2] = __dp4a(px[c], kq[2][g], s[c][2]);
+                        }
+                    }
+                    uint32_t out[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) out[c] = to_u8<kClip>(int32_t(s[c][0] + (s[c][1] << 8) + (s[c][2] << 16)));
+                    tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] = out[0] | (out[1] << 8) | (out[2] << 16);
+                }
+            }
         } else if (col_active) {
             // byte address (in shared memory) of my first source byte of row ra; rows are `pitch` apart
             uint32_t src = smem_u32(sbuf) + uint32_t(uint64_t(ra) * pitch - a0) + 3u * xmin;
@@ -482,12 +544,30 @@ static int pick_bucket(int ksize_h) {
     return 0;
 }
 
+static int pick_quads_bucket(int max_taps) {
+    const int buckets[] = {4, 8, 12, 16, 20, 28, 36};
+    for (int b : buckets)
+        if (max_taps <= b) return b;
+    return 0;
+}
+
 template <int KSH>
 static cudaError_t set_smem_attr(size_t bytes) {
-    const void *fns[4] = {reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, false, false>),
-                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, true, false>),
-                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, false, true>),
-                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, true, true>)};
+    const void *fns[4] = {reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, 0, false>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, 1, false>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, 0, true>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, 1, true>)};
+    for (const void *fn : fns) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+template <int KQ>
+static cudaError_t set_smem_attr_quads(size_t bytes) {
+    const void *fns[2] = {reinterpret_cast<const void *>(resize_bands_kernel<KQ, false, 2, false>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KQ, false, 2, true>)};
     for (const void *fn : fns) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
         if (e != cudaSuccess) return e;
@@ -499,10 +579,17 @@ template <int KSH>
 static void launch_bands(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st, bool planar,
                          bool vparam) {
     const uint32_t grid = n * uint32_t(p.n_bands);
-    if (planar && vparam) resize_bands_kernel<KSH, false, true, true><<<grid, threads, smem, st>>>(p);
-    else if (planar) resize_bands_kernel<KSH, false, true, false><<<grid, threads, smem, st>>>(p);
-    else if (vparam) resize_bands_kernel<KSH, false, false, true><<<grid, threads, smem, st>>>(p);
-    else resize_bands_kernel<KSH, false, false, false><<<grid, threads, smem, st>>>(p);
+    if (planar && vparam) resize_bands_kernel<KSH, false, 1, true><<<grid, threads, smem, st>>>(p);
+    else if (planar) resize_bands_kernel<KSH, false, 1, false><<<grid, threads, smem, st>>>(p);
+    else if (vparam) resize_bands_kernel<KSH, false, 0, true><<<grid, threads, smem, st>>>(p);
+    else resize_bands_kernel<KSH, false, 0, false><<<grid, threads, smem, st>>>(p);
+}
+
+template <int KQ>
+static void launch_quads(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st, bool vparam) {
+    const uint32_t grid = n * uint32_t(p.n_bands);
+    if (vparam) resize_bands_kernel<KQ, false, 2, true><<<grid, threads, smem, st>>>(p);
+    else resize_bands_kernel<KQ, false, 2, false><<<grid, threads, smem, st>>>(p);
 }
 
 }  // namespace b2
@@ -531,6 +618,11 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
     pl->ksh_bucket = pick_bucket(pl->h.ksize);
     pl->threads = ((out_w + 31) / 32) * 32;
     if (pl->threads > 256) pl->ksh_bucket = 0;           // thread-per-column layout: out_w <= 256
+    {
+        int max_taps = 0;
+        for (int x = 0; x < out_w; ++x) max_taps = std::max(max_taps, pl->h.bounds[2 * x + 1]);
+        pl->q_bucket = pl->ksh_bucket != 0 ? pick_quads_bucket(max_taps) : 0;
+    }
     const int pitch = in_w * 3;
     pl->tmp_pitch = ((out_w * 4 + 15) / 16) * 16;
     pl->vparam = out_h * (2 + pl->v.ksize) <= kVtabInts;
@@ -652,6 +744,9 @@ extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint
     // third of its ALU work and is the faster one when a hash kernel shares the SMs.
     bool planar = pl->planar != 0 && (flags & B2_RESIZE_BESIDE_HASH) != 0;
     if (const char *e = getenv("B2_RESIZE_PLANAR")) planar = pl->planar != 0 && atoi(e) != 0;
+    bool quads = false;
+    if (const char *e = getenv("B2_RESIZE_QUADS")) quads = pl->q_bucket != 0 && atoi(e) != 0;
+    if (quads) planar = false;
     const bool fast = pl->ksh_bucket != 0 && resize_path_override() != 1 &&
                       uint64_t(n) * uint64_t(p.n_bands) < 0x7fffffffull;
     if (!fast) {
@@ -663,8 +758,41 @@ extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint
     }
     static std::mutex mu;
     static size_t attr_bytes[64][8];     // [device][bucket index]: largest smem opt-in done so far
+    static size_t attr_bytes_q[64][8];
     int bi = 0;
     cudaError_t e = cudaSuccess;
+    if (quads) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            const int qb = pl->q_bucket;
+            bi = qb <= 20 ? qb / 4 - 1 : (qb == 28 ? 5 : 6);
+            const int dev = pl->device & 63;
+            if (attr_bytes_q[dev][bi] < pl->smem_max) {
+                switch (qb) {
+                    case 4: e = set_smem_attr_quads<4>(pl->smem_max); break;
+                    case 8: e = set_smem_attr_quads<8>(pl->smem_max); break;
+                    case 12: e = set_smem_attr_quads<12>(pl->smem_max); break;
+                    case 16: e = set_smem_attr_quads<16>(pl->smem_max); break;
+                    case 20: e = set_smem_attr_quads<20>(pl->smem_max); break;
+                    case 28: e = set_smem_attr_quads<28>(pl->smem_max); break;
+                    default: e = set_smem_attr_quads<36>(pl->smem_max); break;
+                }
+                if (e == cudaSuccess) attr_bytes_q[dev][bi] = pl->smem_max;
+            }
+        }
+        B2_CUDA_CHECK(e);
+        switch (pl->q_bucket) {
+            case 4: launch_quads<4>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
+            case 8: launch_quads<8>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
+            case 12: launch_quads<12>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
+            case 16: launch_quads<16>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
+            case 20: launch_quads<20>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
+            case 28: launch_quads<28>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
+            default: launch_quads<36>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
+        }
+        B2_LAUNCH_CHECK("resize_bands_kernel<quads>");
+        return B2_OK;
+    }
     {
         std::lock_guard<std::mutex> lock(mu);
         switch (pl->ksh_bucket) {

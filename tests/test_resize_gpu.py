@@ -32,15 +32,16 @@ def _drop_plans():
         p.close()
 
 
-@pytest.fixture(params=["auto", "planar", "generic"])
+@pytest.fixture(params=["auto", "planar", "quads", "generic"])
 def resize_path(request, monkeypatch):
     """auto = the band kernel with the PRMT + IMAD horizontal pass (what a plain call gets); planar = the band
     kernel with the IDP.4A pass forced wherever the shape allows it (what B2_RESIZE_BESIDE_HASH selects);
+    quads = the band kernel with the in-register de-interleave + IDP.4A pass;
     generic = the thread-per-output-pixel fallback.  Plans are cached per shape and read some switches when
     they are created, so the cache is emptied around every case."""
     monkeypatch.setenv("B2_RESIZE_PATH", "1" if request.param == "generic" else "0")
-    if request.param == "planar":
-        monkeypatch.setenv("B2_RESIZE_PLANAR", "1")
+    monkeypatch.setenv("B2_RESIZE_PLANAR", "1" if request.param == "planar" else "0")
+    monkeypatch.setenv("B2_RESIZE_QUADS", "1" if request.param == "quads" else "0")
     _drop_plans()
     yield request.param
     _drop_plans()
