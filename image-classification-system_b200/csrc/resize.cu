@@ -99,6 +99,13 @@ struct b2_resize_plan {
     int q_bucket;         // quads pass: tap capacity (multiple of 4) covering the widest horizontal window; 0 = unavailable
     int planar;           // 1 = the planar IDP.4A horizontal pass applies (in_w % 16 == 0, stage fits the register carry)
     int vparam;           // 1 = the vertical tap table fits the kernel parameters (out_h * (2 + ksize_v) <= kVtabInts)
+    // scatter-form vertical pass (quads pass only): per INPUT row the taps of the <= 3 output rows whose windows
+    // cover it; the intermediate never leaves the registers, so the shared memory is the input ring alone
+    int scat;             // 1 = available (downscale: never more than 3 output rows per input row, one finishing at a time)
+    int4 *d_vscat;        // in_h x {tap of the row in accumulator 0, 1, 2 (row oy lives in accumulator oy % 3),
+                          //         (oy << 2 | accumulator + 1) of the output row that ENDS with this input row, else 0}
+    int rps_scat, stage_bytes_scat;
+    size_t smem_scat;
     size_t smem_fixed;    // ring + intermediate (+ slack); the vertical tap tables add band_rows*(2+ksize_v)*4
     size_t smem_max;      // with band_rows = out_h
 };
@@ -115,6 +122,7 @@ struct ResizeParams {
     uint8_t *thumb;
     float *preview;
     const int32_t *hbounds, *hcoeffs, *vbounds, *vcoeffs;
+    const int4 *vscat;
     int in_h, in_w, out_h, out_w;
     int ksize_h, ksize_v;
     int band_rows, n_bands, max_band_in_rows;
@@ -175,9 +183,18 @@ constexpr int kPlanarChunks = 3;                 // 16-pixel chunks a thread de-
 // per four taps and three channels instead of 12 PRMT + 12 IMAD.  KSH is the tap capacity, a multiple of 4
 // chosen from the widest window the plan actually has (16 for 1080p -> 256, although ksize = 17); any input
 // width and alignment; needs non-negative coefficients (BILINEAR).  Same integers, same result.
-template <int KSH, bool kClip = false, int kMode = 0, bool kVParam = false>
+//
+// kVScat (quads pass only): the vertical pass in scatter form.  A downscale never has more than three output
+// rows whose tap windows cover one input row, and they finish in order, one at a time.  So the thread keeps
+// three rows of accumulators in registers; the horizontal result of an input row (still in registers) is
+// multiplied into them with that input row's three taps (one uniform 16-byte load from a per-plan table),
+// and when the table says a row is complete it is written out and its accumulators start over (row oy lives in
+// accumulator row oy % 3, so nothing rotates).  No
+// intermediate in shared memory, no gather loop: 9 IMAD + 1 load per input row instead of ~40 instructions.
+template <int KSH, bool kClip = false, int kMode = 0, bool kVParam = false, bool kVScat = false>
 __global__ void __launch_bounds__(256)
 resize_bands_kernel(const __grid_constant__ ResizeParams p) {
+    static_assert(!kVScat || kMode == 2, "the scatter-form vertical pass belongs to the quads pass");
     constexpr bool kPlanar = kMode == 1;
     constexpr bool kQuads = kMode == 2;
     constexpr int NQ = (KSH + 3) / 4;           // quads: 4-pixel groups of the window
@@ -215,7 +232,7 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
     }
 
     // vertical taps of this band -> shared memory (unless they came with the kernel parameters)
-    if (!kVParam) {
+    if (!kVParam && !kVScat) {
         for (int i = tid; i < (oy1 - oy0) * 2; i += blockDim.x) vb_s[i] = p.vbounds[2 * oy0 + i];
         for (int i = tid; i < (oy1 - oy0) * p.ksize_v; i += blockDim.x) vk_s[i] = p.vcoeffs[oy0 * p.ksize_v + i];
     }
@@ -349,6 +366,12 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
         next_oy = e1;
     };
 
+    uint32_t va[3][3], vb[3][3];                                     // kVScat: three output rows in flight
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { va[j][c] = uint32_t(kRound); vb[j][c] = 0u; }
+
     // ring position of stage s (buf), of the stage issued this iteration (ibuf) and the parity of buf's
     // barrier are carried along instead of being recomputed with % and / every stage
     int buf = 0, ibuf = p.n_stages - 1;
@@ -430,10 +453,11 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
             }
         } else if constexpr (kQuads) {
             if (col_active) {
+                [[maybe_unused]] const int4 *vsp = p.vscat + ra;
                 uint32_t src = smem_u32(sbuf) + uint32_t(uint64_t(ra) * pitch - a0) + 3u * xmin;
                 for (int r = ra; r < rb; ++r, src += uint32_t(pitch)) {
                     const uint32_t base = src & ~3u;
-                    const uint32_t sh = (src & 3u) * 8u;
+                    const uint32_t sh = src << 3;                          // the funnel shift takes it modulo 32
                     uint32_t w[3 * NQ + 1];
 #pragma unroll
                     for (int j = 0; j < 3 * NQ + 1; ++j)
@@ -460,7 +484,44 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
                     uint32_t out[3];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) out[c] = to_u8<kClip>(int32_t(s[c][0] + (s[c][1] << 8) + (s[c][2] << 16)));
-                    tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] = out[0] | (out[1] << 8) | (out[2] << 16);
+                    if constexpr (kVScat) {
+                        const int4 e = __ldg(vsp++);                       // same address in every thread
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            va[0][c] += out[c] * uint32_t(e.x);
+                            va[1][c] += out[c] * uint32_t(e.y);
+                            va[2][c] += out[c] * uint32_t(e.z);
+                        }
+                        if (e.w) {                                         // uniform: an output row ends with this input row
+                            const int oy = e.w >> 2;
+                            const bool mine = oy >= oy0 && oy < oy1;       // rows of a neighbouring band pass through unwritten
+                            // The accumulators are never reset (a reset on this rarely taken path costs nine register
+                            // moves on the hot one): they run on modulo 2^32 and `b` remembers where the row started.
+                            auto finish = [&](uint32_t (&a)[3], uint32_t (&b)[3]) {
+                                if (mine) {
+                                    const uint32_t o0 = to_u8<kClip>(int32_t(a[0] - b[0])), o1 = to_u8<kClip>(int32_t(a[1] - b[1])),
+                                                   o2 = to_u8<kClip>(int32_t(a[2] - b[2]));
+                                    uint8_t *tpx = thumb + uint32_t(oy) * uint32_t(row_bytes) + 3u * tid;
+                                    tpx[0] = uint8_t(o0); tpx[1] = uint8_t(o1); tpx[2] = uint8_t(o2);
+                                    if (prev) {
+                                        float *pp = prev + uint32_t(oy) * uint32_t(p.out_w) + tid;
+                                        const uint32_t plane = uint32_t(p.out_h) * uint32_t(p.out_w);
+                                        pp[0] = normalise(o0, mean0, istd0);
+                                        pp[plane] = normalise(o1, mean1, istd1);
+                                        pp[2 * plane] = normalise(o2, mean2, istd2);
+                                    }
+                                }
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) b[c] = a[c] - uint32_t(kRound);
+                            };
+                            const int sl = e.w & 3;                        // which accumulator row: (oy % 3) + 1
+                            if (sl == 1) finish(va[0], vb[0]);
+                            else if (sl == 2) finish(va[1], vb[1]);
+                            else finish(va[2], vb[2]);
+                        }
+                    } else {
+                        tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] = out[0] | (out[1] << 8) | (out[2] << 16);
+                    }
                 }
             }
         } else if (col_active) {
@@ -489,7 +550,7 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
             }
         }
         __syncthreads();               // stage consumed (ring slot reusable), intermediate rows visible
-        emit_ready(rb);
+        if constexpr (!kVScat) emit_ready(rb);
         if (++buf == p.n_stages) { buf = 0; parity ^= 1u; }
         if (++ibuf == p.n_stages) ibuf = 0;
     }
@@ -566,8 +627,9 @@ static cudaError_t set_smem_attr(size_t bytes) {
 
 template <int KQ>
 static cudaError_t set_smem_attr_quads(size_t bytes) {
-    const void *fns[2] = {reinterpret_cast<const void *>(resize_bands_kernel<KQ, false, 2, false>),
-                          reinterpret_cast<const void *>(resize_bands_kernel<KQ, false, 2, true>)};
+    const void *fns[3] = {reinterpret_cast<const void *>(resize_bands_kernel<KQ, false, 2, false>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KQ, false, 2, true>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KQ, false, 2, false, true>)};
     for (const void *fn : fns) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
         if (e != cudaSuccess) return e;
@@ -586,9 +648,11 @@ static void launch_bands(const ResizeParams &p, uint32_t n, int threads, size_t 
 }
 
 template <int KQ>
-static void launch_quads(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st, bool vparam) {
+static void launch_quads(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st, bool vparam,
+                         bool vscat) {
     const uint32_t grid = n * uint32_t(p.n_bands);
-    if (vparam) resize_bands_kernel<KQ, false, 2, true><<<grid, threads, smem, st>>>(p);
+    if (vscat) resize_bands_kernel<KQ, false, 2, false, true><<<grid, threads, smem, st>>>(p);
+    else if (vparam) resize_bands_kernel<KQ, false, 2, true><<<grid, threads, smem, st>>>(p);
     else resize_bands_kernel<KQ, false, 2, false><<<grid, threads, smem, st>>>(p);
 }
 
@@ -661,6 +725,52 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
     }
     layout(rps);
     if (pl->smem_max > 220 * 1024) pl->ksh_bucket = 0;       // does not fit at all: generic kernel
+
+    // ---- scatter-form vertical pass: per input row, the taps of output rows oy_lo .. oy_lo + 2, where oy_lo is the
+    // first output row whose window has not ended before this input row.
+    pl->scat = 0; pl->d_vscat = nullptr; pl->rps_scat = 0; pl->stage_bytes_scat = 0; pl->smem_scat = 0;
+    if (pl->q_bucket != 0 && pl->ksh_bucket != 0) {
+        std::vector<int4> tab(size_t(in_h), make_int4(0, 0, 0, 0));
+        bool ok = true;
+        int lo = 0;
+        auto first = [&](int oy) { return pl->v.bounds[2 * oy]; };
+        auto last = [&](int oy) { return pl->v.bounds[2 * oy] + pl->v.bounds[2 * oy + 1] - 1; };
+        for (int oy = 0; oy + 1 < out_h && ok; ++oy) ok = first(oy) <= first(oy + 1) && last(oy) < last(oy + 1);
+        for (int r = 0; r < in_h && ok; ++r) {
+            while (lo < out_h && last(lo) < r) ++lo;
+            int k[3] = {0, 0, 0};                                            // by accumulator row = oy % 3
+            for (int j = 0; j < 3; ++j) {
+                const int oy = lo + j;
+                if (oy < out_h && first(oy) <= r && r <= last(oy)) {
+                    const int c = pl->v.coeffs[size_t(oy) * pl->v.ksize + (r - first(oy))];
+                    if (c < 0) ok = false;
+                    k[oy % 3] = c;
+                }
+            }
+            if (lo + 3 < out_h && first(lo + 3) <= r) ok = false;            // a fourth row would be in flight
+            const bool done = lo < out_h && last(lo) == r;
+            tab[r] = make_int4(k[0], k[1], k[2], done ? (lo << 2) | (lo % 3 + 1) : 0);
+        }
+        if (ok) {
+            int rs = 32;
+            if (const char *e = getenv("B2_RESIZE_RPS")) rs = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : rs;
+            // No intermediate in shared memory, so three CTAs (24 warps) fit an SM with 6-row stages at 1080p: measured
+            // 3.51 ms per 2 368 images against 3.94 ms for two CTAs with 9-row stages; four CTAs (4 rows): 3.51 ms.
+            size_t budget = 74 * 1024;
+            if (const char *e = getenv("B2_RESIZE_SMEM_KB")) budget = size_t(atoi(e)) * 1024;
+            for (; rs >= 1; --rs) {
+                pl->rps_scat = rs;
+                pl->stage_bytes_scat = ((rs * pitch + 32 + overread + 127) / 128) * 128;
+                pl->smem_scat = size_t(pl->n_stages) * pl->stage_bytes_scat + 64;
+                if (pl->smem_scat <= budget) break;
+            }
+            if (rs >= 1 && pl->smem_scat <= 220 * 1024) {
+                B2_CUDA_CHECK(cudaMalloc(&pl->d_vscat, tab.size() * sizeof(int4)));
+                B2_CUDA_CHECK(cudaMemcpy(pl->d_vscat, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice));
+                pl->scat = 1;
+            }
+        }
+    }
     *plan_out = pl;
     return B2_OK;
 }
@@ -668,6 +778,7 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
 extern "C" int b2_resize_plan_destroy(b2_resize_plan *pl) {
     if (!pl) return B2_OK;
     cudaFree(pl->d_hbounds); cudaFree(pl->d_hcoeffs); cudaFree(pl->d_vbounds); cudaFree(pl->d_vcoeffs);
+    if (pl->d_vscat) cudaFree(pl->d_vscat);
     delete pl;
     return B2_OK;
 }
@@ -711,6 +822,7 @@ extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint
     ResizeParams p;
     p.rgb = d_rgb; p.offsets = d_offsets; p.out_slot = d_out_slot; p.thumb = d_thumb; p.preview = d_preview;
     p.hbounds = pl->d_hbounds; p.hcoeffs = pl->d_hcoeffs; p.vbounds = pl->d_vbounds; p.vcoeffs = pl->d_vcoeffs;
+    p.vscat = nullptr;
     p.in_h = pl->in_h; p.in_w = pl->in_w; p.out_h = pl->out_h; p.out_w = pl->out_w;
     p.ksize_h = pl->h.ksize; p.ksize_v = pl->v.ksize;
     // Bands: the whole image per CTA when the batch alone fills the GPU (no input row is read twice);
@@ -744,8 +856,10 @@ extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint
     // third of its ALU work and is the faster one when a hash kernel shares the SMs.
     bool planar = pl->planar != 0 && (flags & B2_RESIZE_BESIDE_HASH) != 0;
     if (const char *e = getenv("B2_RESIZE_PLANAR")) planar = pl->planar != 0 && atoi(e) != 0;
-    bool quads = false;
-    if (const char *e = getenv("B2_RESIZE_QUADS")) quads = pl->q_bucket != 0 && atoi(e) != 0;
+    // The quads pass (IDP.4A on a window de-interleaved in registers) beats both, alone and beside the hash, whenever it
+    // applies; B2_RESIZE_QUADS=0 selects one of the older two (tests and comparisons).
+    bool quads = pl->q_bucket != 0;
+    if (const char *e = getenv("B2_RESIZE_QUADS")) quads = quads && atoi(e) != 0;
     if (quads) planar = false;
     const bool fast = pl->ksh_bucket != 0 && resize_path_override() != 1 &&
                       uint64_t(n) * uint64_t(p.n_bands) < 0x7fffffffull;
@@ -762,33 +876,41 @@ extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint
     int bi = 0;
     cudaError_t e = cudaSuccess;
     if (quads) {
+        bool vscat = pl->scat != 0;
+        if (const char *ev = getenv("B2_RESIZE_VSCAT")) vscat = vscat && atoi(ev) != 0;
+        if (vscat) {
+            p.vscat = pl->d_vscat;
+            p.rows_per_stage = pl->rps_scat; p.stage_bytes = pl->stage_bytes_scat;
+        }
+        const size_t smem_q = vscat ? pl->smem_scat : smem_launch;
+        const size_t smem_attr_q = std::max(pl->smem_max, pl->smem_scat);
         {
             std::lock_guard<std::mutex> lock(mu);
             const int qb = pl->q_bucket;
             bi = qb <= 20 ? qb / 4 - 1 : (qb == 28 ? 5 : 6);
             const int dev = pl->device & 63;
-            if (attr_bytes_q[dev][bi] < pl->smem_max) {
+            if (attr_bytes_q[dev][bi] < smem_attr_q) {
                 switch (qb) {
-                    case 4: e = set_smem_attr_quads<4>(pl->smem_max); break;
-                    case 8: e = set_smem_attr_quads<8>(pl->smem_max); break;
-                    case 12: e = set_smem_attr_quads<12>(pl->smem_max); break;
-                    case 16: e = set_smem_attr_quads<16>(pl->smem_max); break;
-                    case 20: e = set_smem_attr_quads<20>(pl->smem_max); break;
-                    case 28: e = set_smem_attr_quads<28>(pl->smem_max); break;
-                    default: e = set_smem_attr_quads<36>(pl->smem_max); break;
+                    case 4: e = set_smem_attr_quads<4>(smem_attr_q); break;
+                    case 8: e = set_smem_attr_quads<8>(smem_attr_q); break;
+                    case 12: e = set_smem_attr_quads<12>(smem_attr_q); break;
+                    case 16: e = set_smem_attr_quads<16>(smem_attr_q); break;
+                    case 20: e = set_smem_attr_quads<20>(smem_attr_q); break;
+                    case 28: e = set_smem_attr_quads<28>(smem_attr_q); break;
+                    default: e = set_smem_attr_quads<36>(smem_attr_q); break;
                 }
-                if (e == cudaSuccess) attr_bytes_q[dev][bi] = pl->smem_max;
+                if (e == cudaSuccess) attr_bytes_q[dev][bi] = smem_attr_q;
             }
         }
         B2_CUDA_CHECK(e);
         switch (pl->q_bucket) {
-            case 4: launch_quads<4>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
-            case 8: launch_quads<8>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
-            case 12: launch_quads<12>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
-            case 16: launch_quads<16>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
-            case 20: launch_quads<20>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
-            case 28: launch_quads<28>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
-            default: launch_quads<36>(p, n, pl->threads, smem_launch, st, pl->vparam != 0); break;
+            case 4: launch_quads<4>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
+            case 8: launch_quads<8>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
+            case 12: launch_quads<12>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
+            case 16: launch_quads<16>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
+            case 20: launch_quads<20>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
+            case 28: launch_quads<28>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
+            default: launch_quads<36>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
         }
         B2_LAUNCH_CHECK("resize_bands_kernel<quads>");
         return B2_OK;

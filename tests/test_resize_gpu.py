@@ -32,16 +32,18 @@ def _drop_plans():
         p.close()
 
 
-@pytest.fixture(params=["auto", "planar", "quads", "generic"])
+@pytest.fixture(params=["auto", "bands", "planar", "quads-gather", "generic"])
 def resize_path(request, monkeypatch):
-    """auto = the band kernel with the PRMT + IMAD horizontal pass (what a plain call gets); planar = the band
-    kernel with the IDP.4A pass forced wherever the shape allows it (what B2_RESIZE_BESIDE_HASH selects);
-    quads = the band kernel with the in-register de-interleave + IDP.4A pass;
+    """auto = what a plain call gets: the band kernel with the quads horizontal pass (window de-interleaved in
+    registers + IDP.4A) and, for downscales, the scatter-form vertical pass; quads-gather = the same horizontal
+    pass with the gather-form vertical pass (what upscales get); bands = the PRMT + IMAD horizontal pass;
+    planar = the in-place de-interleave + IDP.4A pass wherever the shape allows it;
     generic = the thread-per-output-pixel fallback.  Plans are cached per shape and read some switches when
     they are created, so the cache is emptied around every case."""
     monkeypatch.setenv("B2_RESIZE_PATH", "1" if request.param == "generic" else "0")
     monkeypatch.setenv("B2_RESIZE_PLANAR", "1" if request.param == "planar" else "0")
-    monkeypatch.setenv("B2_RESIZE_QUADS", "1" if request.param == "quads" else "0")
+    monkeypatch.setenv("B2_RESIZE_QUADS", "0" if request.param in ("bands", "planar") else "1")
+    monkeypatch.setenv("B2_RESIZE_VSCAT", "0" if request.param == "quads-gather" else "1")
     _drop_plans()
     yield request.param
     _drop_plans()

@@ -19,11 +19,11 @@ import torch  # noqa: E402
 import ics_b200  # noqa: E402,F401
 from ics_b200 import engine  # noqa: E402
 
-MODES = {"bands": ("0", "0"), "planar": ("1", "0"), "quads": ("0", "1")}
+MODES = {"bands": ("0", "0", "0"), "planar": ("1", "0", "0"), "quads-gather": ("0", "1", "0"), "quads": ("0", "1", "1")}
 
 
 def set_mode(name):
-    os.environ["B2_RESIZE_PLANAR"], os.environ["B2_RESIZE_QUADS"] = MODES[name]
+    os.environ["B2_RESIZE_PLANAR"], os.environ["B2_RESIZE_QUADS"], os.environ["B2_RESIZE_VSCAT"] = MODES[name]
 
 
 def main():
@@ -54,7 +54,10 @@ def main():
         return torch.cuda.Event(enable_timing=True)
 
     ref = None
+    only = os.environ.get("B2_MODES")
     for name in MODES:
+        if only and name not in only.split(","):
+            continue
         set_mode(name)
         run = lambda: plan.run(data, off, thumb=thumb, preview=prev)  # noqa: E731
         run()
@@ -88,7 +91,7 @@ def main():
             e1.record(main)
             torch.cuda.synchronize()
             pair.append(e0.elapsed_time(e1))
-        print(f"{name:7s} alone {ms:.3f} ms = {nb / ms / 1e6:.0f} GB/s   hash + 5 resize: {min(pair):.2f} ms", flush=True)
+        print(f"{name:12s} alone {ms:.3f} ms = {nb / ms / 1e6:.0f} GB/s   hash + 5 resize: {min(pair):.2f} ms", flush=True)
     e0, e1 = ev(), ev()
     e0.record()
     engine.sha256_device(hdata, hoff, hlen, None, hout)

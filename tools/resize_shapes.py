@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Resize throughput over the image shapes of BASELINE configs 1, 3 and 5 (256^2 .. 4096^2, 4K), both horizontal
-passes, ~6 GB of input per shape, outputs 256x256 u8 + f32."""
+"""Resize throughput over the image shapes of BASELINE configs 1, 3 and 5 (256^2 .. 4096^2, 4K), the three horizontal
+passes (quads = the default), ~6 GB of input per shape, outputs 256x256 u8 + f32."""
 import os
 import sys
 
@@ -23,8 +23,9 @@ for (H, W) in [(256, 256), (512, 512), (1024, 1024), (1080, 1920), (2048, 2048),
     thumb = torch.empty((n, 256, 256, 3), dtype=torch.uint8, device=dev)
     prev = torch.empty((n, 3, 256, 256), dtype=torch.float32, device=dev)
     out = []
-    for beside in (False, True):
-        fn = lambda: plan.run(data, off, thumb=thumb, preview=prev, beside_hash=beside)  # noqa: E731
+    for name, (pl_, qd_) in {"quads ": ("0", "1"), "bands ": ("0", "0"), "planar": ("1", "0")}.items():
+        os.environ["B2_RESIZE_PLANAR"], os.environ["B2_RESIZE_QUADS"] = pl_, qd_
+        fn = lambda: plan.run(data, off, thumb=thumb, preview=prev)  # noqa: E731
         fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -35,6 +36,6 @@ for (H, W) in [(256, 256), (512, 512), (1024, 1024), (1080, 1920), (2048, 2048),
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
         b = n * (L + 256 * 256 * 3 * 5)
-        out.append(f"{'planar' if beside else 'bands '} {ms:8.3f} ms {b / ms / 1e6:6.0f} GB/s {n / ms:7.1f} k img/s")
+        out.append(f"{name} {ms:8.3f} ms {b / ms / 1e6:6.0f} GB/s {n / ms:7.1f} k img/s")
     print(f"{H:>4}x{W:<4} n={n:<6} " + "   ".join(out))
     del data, thumb, prev
