@@ -270,7 +270,7 @@ def run_graft(args):
             with torch.cuda.stream(hstream):
                 engine.sha256_device(flat, offsets, lengths, None, digests)
             with torch.cuda.stream(side):
-                plan.run(flat, offsets, thumb=thumbs, preview=previews, beside_hash=True)
+                plan.run(flat, offsets, thumb=thumbs, preview=previews)
             main.wait_stream(hstream)
             main.wait_stream(side)
         else:
@@ -330,7 +330,6 @@ def run_graft(args):
 
     ms_sha = kernel_ms(lambda: engine.sha256_device(flat, offsets, lengths, None, digests))
     ms_resize = kernel_ms(lambda: plan.run(flat, offsets, thumb=thumbs, preview=previews))
-    ms_resize_bh = kernel_ms(lambda: plan.run(flat, offsets, thumb=thumbs, preview=previews, beside_hash=True))
     ms_dedupe = kernel_ms(lambda: engine.dedupe_device(digests))
 
     # sanity check of the timed outputs (sampled images; not timed) against the reference's own host libraries,
@@ -517,10 +516,8 @@ def run_graft(args):
             "kernels": {
                 "sha256_lanes_kernel": roof(sha_bytes, ms_sha, "sha256_lanes_kernel"),
                 "resize_bands_kernel": roof(resize_bytes, ms_resize, "resize_bands_kernel",
-                                            note="alone: the PRMT + IMAD horizontal pass (default of b2_resize_normalize_batch)"),
-                "resize_bands_kernel<planar>": roof(resize_bytes, ms_resize_bh, "resize_bands_kernel<planar>",
-                                                    note="B2_RESIZE_BESIDE_HASH: the IDP.4A horizontal pass used inside the ingest "
-                                                         "step, where the hash owns the ALU pipe; timed alone here"),
+                                            note="timed alone; IDP.4A horizontal pass on a window de-interleaved in registers, "
+                                                 "scatter-form vertical pass in registers, three CTAs per SM"),
                 "dedupe (insert+resolve)": {"ms_per_launch": ms_dedupe, "digests": n_img},
                 "tally_slab_kernel": roof(tally_bytes, ms_tally, "tally_slab_kernel"),
             },

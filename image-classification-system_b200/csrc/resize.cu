@@ -8,16 +8,26 @@
 //   fixed point (int(0.5 + w * 2^22)); out = clip8((2^21 + sum px*k) >> 22);
 //   HORIZONTAL pass first into a uint8 intermediate, then the VERTICAL pass.
 //
-// resize_bands_kernel<KSH> — the product kernel.  One CTA = one band of output rows of one
-// image.  The band's input rows are a single contiguous byte range of the HWC image; the
-// bulk-copy (TMA) engine streams it through a ring of shared-memory stages (cp.async.bulk +
-// mbarrier), so global memory is read once, in large aligned bursts, with no register
-// staging.  Thread x owns output column x: its KSH horizontal taps live in registers for the
-// whole band; per input row it pulls its ~3*KSH source bytes from shared memory as 32-bit
-// words, funnel-shifts them to a byte-aligned window and runs the integer MACs, writing the
-// 3-byte intermediate into a shared-memory tile.  After the last stage the CTA runs the
-// vertical pass out of that tile and writes the uint8 HWC thumbnail (32-bit stores) and the
-// float32 CHW preview.  No tensor cores: 2 MAC per input byte, nothing to contract.
+// resize_bands_kernel<KQ, kVMode> — the product kernel.  One CTA = one band of output rows of one
+// image (the whole image when the batch fills the GPU).  The band's input rows are a single contiguous byte
+// range of the HWC image; the bulk-copy (TMA) engine streams it through a ring of shared-memory stages
+// (cp.async.bulk + an mbarrier per stage), so global memory is read once, in large aligned bursts, with no
+// register staging.
+//   Horizontal pass ("quads"): thread x owns output column x.  Per input row it pulls its byte-aligned window
+// from shared memory as 32-bit words (funnel-shifted), de-interleaves it IN REGISTERS — four pixels = three
+// words -> one R, one G and one B word, two PRMT each — and every plane word meets three coefficient-limb
+// words (a 22-bit tap = three 8-bit limbs) in three IDP.4A: 6 PRMT + 9 IDP.4A per four taps and three
+// channels.  KQ is the tap capacity, a multiple of 4 chosen from the widest window the plan has (16 for
+// 1080p -> 256).  Any input width and alignment; taps are non-negative (BILINEAR).
+//   Vertical pass, scatter form (kVMode 2, every downscale): never more than three output rows have tap
+// windows over one input row, and they finish in order.  The thread keeps three rows of accumulators; the
+// horizontal result of an input row, still in registers, is multiplied into them with that row's three taps
+// (one uniform 16-byte load from a per-plan table); when the table says a row is complete it is written out
+// (uint8 HWC thumbnail + float32 CHW preview).  No intermediate in shared memory: three CTAs per SM.
+//   Vertical pass, gather form (kVMode 0 / 1, upscales): the horizontal results go to a rolling,
+// thread-private shared-memory intermediate and finished output rows gather their taps from it; the tap
+// table travels in the kernel parameters when it fits (kVMode 1), else it is staged in shared memory.
+// No tensor cores: 2 MAC per input byte, nothing to contract.
 //
 // resize_generic_kernel — any shape / any alignment, one thread per output pixel, straight
 // from global memory.  Used when the fast path's limits do not hold, and by the tests as an
@@ -89,25 +99,23 @@ struct b2_resize_plan {
     int device;
     int32_t *d_hbounds, *d_hcoeffs, *d_vbounds, *d_vcoeffs;
     // fast-path geometry
+    int threads;
+    int q_bucket;         // tap capacity (multiple of 4) covering the widest horizontal window; 0 = generic kernel only
+    int n_stages;
+    // gather-form vertical pass
+    int vparam;           // 1 = the vertical tap table fits the kernel parameters (out_h * (2 + ksize_v) <= kVtabInts)
     int tmp_ring_rows;    // rows of the rolling intermediate (power of two)
+    int tmp_pitch;        // bytes per intermediate row (multiple of 16)
     int rows_per_stage;
     int stage_bytes;      // bytes of one ring stage (incl. alignment + over-read padding)
-    int n_stages;
-    int tmp_pitch;        // bytes per intermediate row (multiple of 16)
-    int threads;
-    int ksh_bucket;       // template bucket for horizontal taps (0 = fast path unavailable)
-    int q_bucket;         // quads pass: tap capacity (multiple of 4) covering the widest horizontal window; 0 = unavailable
-    int planar;           // 1 = the planar IDP.4A horizontal pass applies (in_w % 16 == 0, stage fits the register carry)
-    int vparam;           // 1 = the vertical tap table fits the kernel parameters (out_h * (2 + ksize_v) <= kVtabInts)
-    // scatter-form vertical pass (quads pass only): per INPUT row the taps of the <= 3 output rows whose windows
-    // cover it; the intermediate never leaves the registers, so the shared memory is the input ring alone
+    size_t smem_fixed;    // ring + intermediate (+ slack); staged vertical tap tables add band_rows*(2+ksize_v)*4
+    size_t smem_max;      // with band_rows = out_h
+    // scatter-form vertical pass: per INPUT row the taps of the <= 3 output rows whose windows cover it
     int scat;             // 1 = available (downscale: never more than 3 output rows per input row, one finishing at a time)
     int4 *d_vscat;        // in_h x {tap of the row in accumulator 0, 1, 2 (row oy lives in accumulator oy % 3),
                           //         (oy << 2 | accumulator + 1) of the output row that ENDS with this input row, else 0}
     int rps_scat, stage_bytes_scat;
     size_t smem_scat;
-    size_t smem_fixed;    // ring + intermediate (+ slack); the vertical tap tables add band_rows*(2+ksize_v)*4
-    size_t smem_max;      // with band_rows = out_h
 };
 
 namespace b2 {
@@ -125,10 +133,10 @@ struct ResizeParams {
     const int4 *vscat;
     int in_h, in_w, out_h, out_w;
     int ksize_h, ksize_v;
-    int band_rows, n_bands, max_band_in_rows;
+    int band_rows, n_bands;
     int rows_per_stage, stage_bytes, n_stages, tmp_pitch, tmp_ring_rows;
     float mean[3], inv_std[3];
-    // kVParam kernels: the vertical taps of every output row, {first, count, k_0 .. k_{ksize_v-1}} per row, travel
+    // kVMode 1: the vertical taps of every output row, {first, count, k_0 .. k_{ksize_v-1}} per row, travel
     // in the kernel parameters (constant bank, uniform loads: no shared-memory traffic, no staging at CTA start).
     int32_t vtab[kVtabInts];
 };
@@ -144,62 +152,17 @@ __device__ __forceinline__ float normalise(uint32_t u8, float mean, float inv_st
     return __fmul_rn(__fsub_rn(__fmul_rn(float(u8), 1.0f / 255.0f), mean), inv_std);
 }
 
-// BILINEAR taps are non-negative and sum to 2^22 +- ksize/2, so 2^21 + sum(px*k) >> 22 is already inside
-// 0..255 and the clip is dead code; kClip = true keeps it for filters with negative lobes.
-template <bool kClip>
-__device__ __forceinline__ uint32_t to_u8(int32_t acc) {
-    return kClip ? clip8(acc) : uint32_t(acc) >> kPrecisionBits;
-}
+// BILINEAR taps are non-negative and sum to 2^22 +- ksize/2, so (2^21 + sum(px*k)) >> 22 is already inside
+// 0..255: the band kernel needs no clip (the generic kernel keeps Pillow's).
+__device__ __forceinline__ uint32_t to_u8(uint32_t acc) { return acc >> kPrecisionBits; }
 
-// De-interleave 16 RGB pixels (48 bytes, 12 words) into 16 R, 16 G and 16 B bytes: two PRMT per output word.
-__device__ __forceinline__ void planarize16(const uint4 (&in)[3], uint4 &r, uint4 &g, uint4 &b) {
-    const uint32_t w[12] = {in[0].x, in[0].y, in[0].z, in[0].w, in[1].x, in[1].y, in[1].z, in[1].w,
-                            in[2].x, in[2].y, in[2].z, in[2].w};
-    uint32_t rr[4], gg[4], bb[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {                // pixels 4q..4q+3 = bytes 0..11 of (w0, w1, w2)
-        const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
-        rr[q] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);     // bytes 0, 3, 6, 9
-        gg[q] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);     // bytes 1, 4, 7, 10
-        bb[q] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);     // bytes 2, 5, 8, 11
-    }
-    r = make_uint4(rr[0], rr[1], rr[2], rr[3]);
-    g = make_uint4(gg[0], gg[1], gg[2], gg[3]);
-    b = make_uint4(bb[0], bb[1], bb[2], bb[3]);
-}
-
-constexpr int kPlanarChunks = 3;                 // 16-pixel chunks a thread de-interleaves per stage (registers)
-
-// kPlanar: the stage is de-interleaved IN PLACE into an R, a G and a B plane (each thread carries up to
-// kPlanarChunks 48-byte chunks through registers across one barrier), and the horizontal taps run as
-// IDP.4A dot products of four plane bytes with four 8-bit coefficient limbs (a 22-bit coefficient = three
-// limbs, recombined with two shift-adds per output; 8-byte aligned windows read with LDS.64): ~80 instructions
-// per thread and input row instead of ~140 (one PRMT + one IMAD per byte-tap), a third of them on the ALU pipe.  Needs in_w % 16 == 0 (rows are whole 48-byte chunks and start
-// 16-byte aligned) and non-negative coefficients (BILINEAR).  Same integers, same result.
-//
-// kMode 2 ("quads"): no shared-memory round trip at all.  The thread's byte-aligned window (funnel-shifted as
-// in the bands pass) is de-interleaved IN REGISTERS, four pixels = three words -> one R, one G and one B word
-// (two PRMT each), and every plane word meets three coefficient-limb words in three IDP.4A: 6 PRMT + 9 IDP.4A
-// per four taps and three channels instead of 12 PRMT + 12 IMAD.  KSH is the tap capacity, a multiple of 4
-// chosen from the widest window the plan actually has (16 for 1080p -> 256, although ksize = 17); any input
-// width and alignment; needs non-negative coefficients (BILINEAR).  Same integers, same result.
-//
-// kVScat (quads pass only): the vertical pass in scatter form.  A downscale never has more than three output
-// rows whose tap windows cover one input row, and they finish in order, one at a time.  So the thread keeps
-// three rows of accumulators in registers; the horizontal result of an input row (still in registers) is
-// multiplied into them with that input row's three taps (one uniform 16-byte load from a per-plan table),
-// and when the table says a row is complete it is written out and its accumulators start over (row oy lives in
-// accumulator row oy % 3, so nothing rotates).  No
-// intermediate in shared memory, no gather loop: 9 IMAD + 1 load per input row instead of ~40 instructions.
-template <int KSH, bool kClip = false, int kMode = 0, bool kVParam = false, bool kVScat = false>
+template <int KQ, int kVMode>
 __global__ void __launch_bounds__(256)
 resize_bands_kernel(const __grid_constant__ ResizeParams p) {
-    static_assert(!kVScat || kMode == 2, "the scatter-form vertical pass belongs to the quads pass");
-    constexpr bool kPlanar = kMode == 1;
-    constexpr bool kQuads = kMode == 2;
-    constexpr int NQ = (KSH + 3) / 4;           // quads: 4-pixel groups of the window
-    constexpr int NV = (3 * KSH + 3) / 4;       // byte-aligned window, in 32-bit words
-    constexpr int NW = 2 * ((KSH + 7 + 7) / 8); // planar: 8-byte aligned window of one plane, in 32-bit words (LDS.64)
+    constexpr bool kVScat = kVMode == 2;
+    constexpr bool kVParam = kVMode == 1;
+    constexpr int NQ = KQ / 4;                  // 4-pixel groups of the window
+    static_assert(KQ % 4 == 0, "tap capacity is a whole number of quads");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
 
@@ -218,11 +181,12 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(img_ptr)) & 15) == 0;
 
     uint8_t *ring = smem;                                            // n_stages * stage_bytes
-    // rolling intermediate: tmp_ring_rows rows of one packed RGBX word per output column
+    // gather form: rolling intermediate of tmp_ring_rows rows, one packed RGBX word per output column; column x is
+    // written and read by thread x only
     uint32_t *tmp = reinterpret_cast<uint32_t *>(smem + size_t(p.n_stages) * p.stage_bytes);
     const int tmp_pitch_w = p.tmp_pitch >> 2;
     int32_t *vb_s = reinterpret_cast<int32_t *>(smem + size_t(p.n_stages) * p.stage_bytes +
-                                                size_t(p.tmp_ring_rows) * p.tmp_pitch);            // band_rows*2 (!kVParam)
+                                                size_t(p.tmp_ring_rows) * p.tmp_pitch);            // band_rows*2 (kVMode 0)
     int32_t *vk_s = vb_s + 2 * p.band_rows;                          // band_rows * ksize_v
     const int tmp_mask = p.tmp_ring_rows - 1;                        // power of two
 
@@ -230,58 +194,27 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
         for (int s = 0; s < p.n_stages; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
-
-    // vertical taps of this band -> shared memory (unless they came with the kernel parameters)
-    if (!kVParam && !kVScat) {
+    if (kVMode == 0) {                 // vertical taps of this band -> shared memory
         for (int i = tid; i < (oy1 - oy0) * 2; i += blockDim.x) vb_s[i] = p.vbounds[2 * oy0 + i];
         for (int i = tid; i < (oy1 - oy0) * p.ksize_v; i += blockDim.x) vk_s[i] = p.vcoeffs[oy0 * p.ksize_v + i];
     }
 
-    // horizontal taps of my column -> registers
+    // horizontal taps of my column -> registers: limb i of the taps under pixels 4g .. 4g+3 of my window
     const bool col_active = tid < p.out_w;
-    int xmin = 0;
-    int32_t kh[KSH];                               // bands pass (unused, hence free, in the planar instantiations)
-    // planar: coefficient limbs laid out against the 8-byte aligned window that starts at pixel xmin & ~7
-    uint32_t kl[3][NW];                            // planar pass
-    uint32_t kq[3][NQ];                            // quads pass: limb i of the taps under pixels 4g .. 4g+3
-    if (col_active) xmin = p.hbounds[2 * tid];
-    if constexpr (kQuads) {
+    const int xmin = col_active ? p.hbounds[2 * tid] : 0;
+    uint32_t kq[3][NQ];
 #pragma unroll
-        for (int g = 0; g < NQ; ++g) {
-            uint32_t l0 = 0, l1 = 0, l2 = 0;
+    for (int g = 0; g < NQ; ++g) {
+        uint32_t l0 = 0, l1 = 0, l2 = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int t = 4 * g + b;
-                const uint32_t k = (col_active && t < p.ksize_h) ? uint32_t(p.hcoeffs[tid * p.ksize_h + t]) : 0u;
-                l0 |= (k & 0xffu) << (8 * b);
-                l1 |= ((k >> 8) & 0xffu) << (8 * b);
-                l2 |= ((k >> 16) & 0xffu) << (8 * b);
-            }
-            kq[0][g] = l0; kq[1][g] = l1; kq[2][g] = l2;
+        for (int b = 0; b < 4; ++b) {
+            const int t = 4 * g + b;
+            const uint32_t k = (col_active && t < p.ksize_h) ? uint32_t(p.hcoeffs[tid * p.ksize_h + t]) : 0u;
+            l0 |= (k & 0xffu) << (8 * b);
+            l1 |= ((k >> 8) & 0xffu) << (8 * b);
+            l2 |= ((k >> 16) & 0xffu) << (8 * b);
         }
-    } else if constexpr (!kPlanar) {
-#pragma unroll
-        for (int t = 0; t < KSH; ++t) kh[t] = 0;
-        if (col_active) {
-#pragma unroll
-            for (int t = 0; t < KSH; ++t)
-                if (t < p.ksize_h) kh[t] = p.hcoeffs[tid * p.ksize_h + t];
-        }
-    } else {
-        const int off = xmin & 7;
-#pragma unroll
-        for (int j = 0; j < NW; ++j) {
-            uint32_t l0 = 0, l1 = 0, l2 = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int t = 4 * j + b - off;                     // tap under byte b of window word j
-                const uint32_t k = (col_active && t >= 0 && t < p.ksize_h) ? uint32_t(p.hcoeffs[tid * p.ksize_h + t]) : 0u;
-                l0 |= (k & 0xffu) << (8 * b);
-                l1 |= ((k >> 8) & 0xffu) << (8 * b);
-                l2 |= ((k >> 16) & 0xffu) << (8 * b);
-            }
-            kl[0][j] = l0; kl[1][j] = l1; kl[2][j] = l2;
-        }
+        kq[0][g] = l0; kq[1][g] = l1; kq[2][g] = l2;
     }
     __syncthreads();
 
@@ -317,20 +250,30 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
         for (int s = 0; s < p.n_stages - 1 && s < total_stages; ++s) issue(s, s);
     }
 
-    // ---- vertical pass, run incrementally: after every stage the output rows whose taps are all in
-    // the rolling intermediate are finished and written.  The intermediate is a ring of tmp_ring_rows
-    // (>= 2*rows_per_stage + ksize_v + 2) rows, so a band can be the whole image: no input row is read
-    // or filtered twice, and the next stage's horizontal pass never overwrites a row still being read.
     const int row_bytes = p.out_w * 3;
     const uint32_t slot = p.out_slot ? p.out_slot[img] : uint32_t(img);
-    uint8_t *thumb = p.thumb + uint64_t(slot) * p.out_h * row_bytes;
-    float *prev = p.preview ? p.preview + uint64_t(slot) * 3 * p.out_h * p.out_w : nullptr;
-    int next_oy = oy0;                                               // uniform: first output row not yet written
-    // One thread per output PIXEL (thread x = column x, as in the horizontal pass): every warp gets the
-    // same share of a finished row, so nobody idles at the per-stage barrier, and the float32 CHW
-    // preview is written with fully coalesced 128-byte stores.
+    uint8_t *thumb_px = p.thumb + uint64_t(slot) * p.out_h * row_bytes + 3 * tid;                     // my column, row 0
+    float *prev_px = p.preview ? p.preview + uint64_t(slot) * 3 * p.out_h * p.out_w + tid : nullptr;
+    const uint32_t plane = uint32_t(p.out_h) * uint32_t(p.out_w);
     const float mean0 = p.mean[0], mean1 = p.mean[1], mean2 = p.mean[2];
     const float istd0 = p.inv_std[0], istd1 = p.inv_std[1], istd2 = p.inv_std[2];
+    // One thread per output PIXEL: the float32 CHW preview is written with fully coalesced 128-byte stores.
+    auto write_pixel = [&](int oy, uint32_t o0, uint32_t o1, uint32_t o2) {
+        uint8_t *tpx = thumb_px + uint32_t(oy) * uint32_t(row_bytes);
+        tpx[0] = uint8_t(o0); tpx[1] = uint8_t(o1); tpx[2] = uint8_t(o2);
+        if (prev_px) {
+            float *pp = prev_px + uint32_t(oy) * uint32_t(p.out_w);
+            pp[0] = normalise(o0, mean0, istd0);
+            pp[plane] = normalise(o1, mean1, istd1);
+            pp[2 * plane] = normalise(o2, mean2, istd2);
+        }
+    };
+
+    // ---- gather-form vertical pass, run incrementally: after every stage the output rows whose taps are all in
+    // the rolling intermediate are finished and written.  The intermediate is a ring of tmp_ring_rows
+    // (>= rows_per_stage + ksize_v + 2) rows, so a band can be the whole image: no input row is read or
+    // filtered twice.
+    int next_oy = oy0;                                               // first output row not yet written
     const int vstride = 2 + p.ksize_v;
     auto v_first = [&](int oy) { return kVParam ? p.vtab[oy * vstride] : vb_s[2 * (oy - oy0)]; };
     auto v_count = [&](int oy) { return kVParam ? p.vtab[oy * vstride + 1] : vb_s[2 * (oy - oy0) + 1]; };
@@ -341,39 +284,33 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
         if (col_active) {
             for (int oy = next_oy; oy < e1; ++oy) {
                 const int cnt = v_count(oy);
-                int32_t a0 = kRound, a1 = kRound, a2 = kRound;
+                uint32_t a0 = kRound, a1 = kRound, a2 = kRound;
                 const uint32_t *col = tmp + tid;
                 int rr = v_first(oy) - r0;
                 for (int t = 0; t < cnt; ++t, ++rr) {
                     const uint32_t px = col[size_t(rr & tmp_mask) * tmp_pitch_w];     // one RGBX word per tap
-                    const int32_t k = v_coeff(oy, t);                                  // uniform: constant bank or broadcast
-                    a0 += int32_t(px & 0xffu) * k;
-                    a1 += int32_t(__byte_perm(px, 0, 0x4441)) * k;
-                    a2 += int32_t(__byte_perm(px, 0, 0x4442)) * k;
+                    const uint32_t k = uint32_t(v_coeff(oy, t));                       // uniform: constant bank or broadcast
+                    a0 += (px & 0xffu) * k;
+                    a1 += __byte_perm(px, 0, 0x4441) * k;
+                    a2 += __byte_perm(px, 0, 0x4442) * k;
                 }
-                const uint32_t o0 = to_u8<kClip>(a0), o1 = to_u8<kClip>(a1), o2 = to_u8<kClip>(a2);
-                uint8_t *tpx = thumb + size_t(oy) * row_bytes + 3 * tid;
-                tpx[0] = uint8_t(o0); tpx[1] = uint8_t(o1); tpx[2] = uint8_t(o2);
-                if (prev) {
-                    float *pp = prev + size_t(oy) * p.out_w + tid;
-                    const size_t plane = size_t(p.out_h) * p.out_w;
-                    pp[0] = normalise(o0, mean0, istd0);
-                    pp[plane] = normalise(o1, mean1, istd1);
-                    pp[2 * plane] = normalise(o2, mean2, istd2);
-                }
+                write_pixel(oy, to_u8(a0), to_u8(a1), to_u8(a2));
             }
         }
         next_oy = e1;
     };
 
-    uint32_t va[3][3], vb[3][3];                                     // kVScat: three output rows in flight
+    // ---- scatter-form vertical pass: three output rows in flight.  The accumulators are never reset (a reset on the
+    // rarely taken "row complete" path costs nine register moves on the hot one): they run on modulo 2^32 and
+    // vb remembers where the row in that accumulator started.
+    uint32_t va[3][3], vb[3][3];
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
         for (int c = 0; c < 3; ++c) { va[j][c] = uint32_t(kRound); vb[j][c] = 0u; }
 
-    // ring position of stage s (buf), of the stage issued this iteration (ibuf) and the parity of buf's
-    // barrier are carried along instead of being recomputed with % and / every stage
+    // ring position of stage s (buf), of the stage issued this iteration (ibuf) and the parities of their
+    // barriers are carried along instead of being recomputed with % and / every stage
     int buf = 0, ibuf = p.n_stages - 1;
     uint32_t parity = 0;
     for (int s = 0; s < total_stages; ++s) {
@@ -382,10 +319,8 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
         stage_range(s, b0, b1);
         const uint64_t a0 = b0 & ~uint64_t(15);
         if (aligned) {
-            if (tid == 0 && s + p.n_stages - 1 < total_stages) {
-                if (kPlanar) fence_proxy_async();   // the slot was last written by ordinary stores (the planes)
-                issue(s + p.n_stages - 1, ibuf);
-            }
+            // slot ibuf held stage s - 1, which every warp left behind at the barrier that ended the last iteration
+            if (tid == 0 && s + p.n_stages - 1 < total_stages) issue(s + p.n_stages - 1, ibuf);
             mbar_wait(&full_bar[buf], parity);
             const uint64_t lim = img_bytes & ~uint64_t(15);
             if (b1 > lim) {            // ragged image tail: uniform branch, last stage of last band
@@ -399,157 +334,69 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
 
         const int ra = r0 + s * p.rows_per_stage;
         const int rb = min(ra + p.rows_per_stage, r1);
-        if constexpr (kPlanar) {
-            // ---- de-interleave the stage in place: chunk i of the stage (16 pixels, 48 bytes) becomes 16 bytes of
-            // each plane at offset 16 i; a plane holds (rb - ra) rows of in_w bytes, rows contiguous.
-            const uint32_t n_chunks = uint32_t(rb - ra) * uint32_t(p.in_w >> 4);
-            const uint32_t plane_bytes = uint32_t(rb - ra) * uint32_t(p.in_w);
-            uint4 ch[kPlanarChunks][3];
-#pragma unroll
-            for (int i = 0; i < kPlanarChunks; ++i) {
-                const uint32_t idx = tid + i * blockDim.x;
-                if (idx < n_chunks) {
-                    const uint4 *src4 = reinterpret_cast<const uint4 *>(sbuf + size_t(idx) * 48);
-                    ch[i][0] = src4[0]; ch[i][1] = src4[1]; ch[i][2] = src4[2];
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < kPlanarChunks; ++i) {
-                const uint32_t idx = tid + i * blockDim.x;
-                if (idx < n_chunks) {
-                    uint4 r4, g4, b4;
-                    planarize16(ch[i], r4, g4, b4);
-                    *reinterpret_cast<uint4 *>(sbuf + size_t(idx) * 16) = r4;
-                    *reinterpret_cast<uint4 *>(sbuf + plane_bytes + size_t(idx) * 16) = g4;
-                    *reinterpret_cast<uint4 *>(sbuf + 2 * plane_bytes + size_t(idx) * 16) = b4;
-                }
-            }
-            fence_proxy_async();           // my plane stores are ordered before the bulk copy that refills this slot later
-            __syncthreads();
-            if (col_active) {
-                const uint8_t *src = sbuf + (xmin & ~7);
-                for (int r = ra; r < rb; ++r, src += p.in_w) {
-                    uint32_t out[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        uint32_t w[NW];
-#pragma unroll
-                        for (int j = 0; j < NW; j += 2) {
-                            const uint2 q = *reinterpret_cast<const uint2 *>(src + size_t(c) * plane_bytes + 4 * j);
-                            w[j] = q.x; w[j + 1] = q.y;
-                        }
-                        uint32_t s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-                        for (int j = 0; j < NW; ++j) {
-                            s0 = __dp4a(w[j], kl[0][j], s0);
-                            s1 = __dp4a(w[j], kl[1][j], s1);
-                            s2 = __dp4a(w[j], kl[2][j], s2);
-                        }
-                        out[c] = to_u8<kClip>(int32_t(uint32_t(kRound) + s0 + (s1 << 8) + (s2 << 16)));
-                    }
-                    tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] = out[0] | (out[1] << 8) | (out[2] << 16);
-                }
-            }
-        } else if constexpr (kQuads) {
-            if (col_active) {
-                [[maybe_unused]] const int4 *vsp = p.vscat + ra;
-                uint32_t src = smem_u32(sbuf) + uint32_t(uint64_t(ra) * pitch - a0) + 3u * xmin;
-                for (int r = ra; r < rb; ++r, src += uint32_t(pitch)) {
-                    const uint32_t base = src & ~3u;
-                    const uint32_t sh = src << 3;                          // the funnel shift takes it modulo 32
-                    uint32_t w[3 * NQ + 1];
-#pragma unroll
-                    for (int j = 0; j < 3 * NQ + 1; ++j)
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[j]) : "r"(base + 4u * j));
-                    uint32_t s[3][3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) { s[c][0] = uint32_t(kRound); s[c][1] = 0; s[c][2] = 0; }
-#pragma unroll
-                    for (int g = 0; g < NQ; ++g) {
-                        const uint32_t w0 = __funnelshift_r(w[3 * g], w[3 * g + 1], sh);
-                        const uint32_t w1 = __funnelshift_r(w[3 * g + 1], w[3 * g + 2], sh);
-                        const uint32_t w2 = __funnelshift_r(w[3 * g + 2], w[3 * g + 3], sh);
-                        uint32_t px[3];
-                        px[0] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);     // R of pixels 4g .. 4g+3
-                        px[1] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);     // G
-                        px[2] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);     // B
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            s[c][0] = __dp4a(px[c], kq[0][g], s[c][0]);
-                            s[c][1] = __dp4a(px[c], kq[1][g], s[c][1]);
-                            s[c][2] = __dp4a(px[c], kq[2][g], s[c][2]);
-                        }
-                    }
-                    uint32_t out[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) out[c] = to_u8<kClip>(int32_t(s[c][0] + (s[c][1] << 8) + (s[c][2] << 16)));
-                    if constexpr (kVScat) {
-                        const int4 e = __ldg(vsp++);                       // same address in every thread
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            va[0][c] += out[c] * uint32_t(e.x);
-                            va[1][c] += out[c] * uint32_t(e.y);
-                            va[2][c] += out[c] * uint32_t(e.z);
-                        }
-                        if (e.w) {                                         // uniform: an output row ends with this input row
-                            const int oy = e.w >> 2;
-                            const bool mine = oy >= oy0 && oy < oy1;       // rows of a neighbouring band pass through unwritten
-                            // The accumulators are never reset (a reset on this rarely taken path costs nine register
-                            // moves on the hot one): they run on modulo 2^32 and `b` remembers where the row started.
-                            auto finish = [&](uint32_t (&a)[3], uint32_t (&b)[3]) {
-                                if (mine) {
-                                    const uint32_t o0 = to_u8<kClip>(int32_t(a[0] - b[0])), o1 = to_u8<kClip>(int32_t(a[1] - b[1])),
-                                                   o2 = to_u8<kClip>(int32_t(a[2] - b[2]));
-                                    uint8_t *tpx = thumb + uint32_t(oy) * uint32_t(row_bytes) + 3u * tid;
-                                    tpx[0] = uint8_t(o0); tpx[1] = uint8_t(o1); tpx[2] = uint8_t(o2);
-                                    if (prev) {
-                                        float *pp = prev + uint32_t(oy) * uint32_t(p.out_w) + tid;
-                                        const uint32_t plane = uint32_t(p.out_h) * uint32_t(p.out_w);
-                                        pp[0] = normalise(o0, mean0, istd0);
-                                        pp[plane] = normalise(o1, mean1, istd1);
-                                        pp[2 * plane] = normalise(o2, mean2, istd2);
-                                    }
-                                }
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) b[c] = a[c] - uint32_t(kRound);
-                            };
-                            const int sl = e.w & 3;                        // which accumulator row: (oy % 3) + 1
-                            if (sl == 1) finish(va[0], vb[0]);
-                            else if (sl == 2) finish(va[1], vb[1]);
-                            else finish(va[2], vb[2]);
-                        }
-                    } else {
-                        tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] = out[0] | (out[1] << 8) | (out[2] << 16);
-                    }
-                }
-            }
-        } else if (col_active) {
+        if (col_active) {
+            [[maybe_unused]] const int4 *vsp = p.vscat + ra;
             // byte address (in shared memory) of my first source byte of row ra; rows are `pitch` apart
             uint32_t src = smem_u32(sbuf) + uint32_t(uint64_t(ra) * pitch - a0) + 3u * xmin;
             for (int r = ra; r < rb; ++r, src += uint32_t(pitch)) {
                 const uint32_t base = src & ~3u;
-                const uint32_t sh = (src & 3u) * 8u;
-                uint32_t w[NV + 1];
+                const uint32_t sh = src << 3;                          // the funnel shift takes it modulo 32
+                uint32_t w[3 * NQ + 1];
 #pragma unroll
-                for (int j = 0; j < NV + 1; ++j)
+                for (int j = 0; j < 3 * NQ + 1; ++j)
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[j]) : "r"(base + 4u * j));
-                uint32_t v[NV];
+                uint32_t acc[3][3];
 #pragma unroll
-                for (int j = 0; j < NV; ++j) v[j] = __funnelshift_r(w[j], w[j + 1], sh);
-                int32_t acc0 = kRound, acc1 = kRound, acc2 = kRound;
+                for (int c = 0; c < 3; ++c) { acc[c][0] = uint32_t(kRound); acc[c][1] = 0; acc[c][2] = 0; }
 #pragma unroll
-                for (int t = 0; t < KSH; ++t) {
-                    const int q0 = 3 * t, q1 = 3 * t + 1, q2 = 3 * t + 2;
-                    acc0 += int32_t(__byte_perm(v[q0 >> 2], 0, 0x4440 | (q0 & 3))) * kh[t];
-                    acc1 += int32_t(__byte_perm(v[q1 >> 2], 0, 0x4440 | (q1 & 3))) * kh[t];
-                    acc2 += int32_t(__byte_perm(v[q2 >> 2], 0, 0x4440 | (q2 & 3))) * kh[t];
+                for (int g = 0; g < NQ; ++g) {
+                    const uint32_t w0 = __funnelshift_r(w[3 * g], w[3 * g + 1], sh);
+                    const uint32_t w1 = __funnelshift_r(w[3 * g + 1], w[3 * g + 2], sh);
+                    const uint32_t w2 = __funnelshift_r(w[3 * g + 2], w[3 * g + 3], sh);
+                    uint32_t px[3];
+                    px[0] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);     // R of pixels 4g .. 4g+3
+                    px[1] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);     // G
+                    px[2] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);     // B
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        acc[c][0] = __dp4a(px[c], kq[0][g], acc[c][0]);
+                        acc[c][1] = __dp4a(px[c], kq[1][g], acc[c][1]);
+                        acc[c][2] = __dp4a(px[c], kq[2][g], acc[c][2]);
+                    }
                 }
-                tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] =
-                    to_u8<kClip>(acc0) | (to_u8<kClip>(acc1) << 8) | (to_u8<kClip>(acc2) << 16);
+                uint32_t out[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) out[c] = to_u8(acc[c][0] + (acc[c][1] << 8) + (acc[c][2] << 16));
+                if constexpr (kVScat) {
+                    const int4 e = __ldg(vsp++);                       // same address in every thread
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        va[0][c] += out[c] * uint32_t(e.x);
+                        va[1][c] += out[c] * uint32_t(e.y);
+                        va[2][c] += out[c] * uint32_t(e.z);
+                    }
+                    if (e.w) {                                         // uniform: an output row ends with this input row
+                        const int oy = e.w >> 2;
+                        const bool mine = oy >= oy0 && oy < oy1;       // rows of a neighbouring band pass through unwritten
+                        auto finish = [&](uint32_t (&a)[3], uint32_t (&b)[3]) {
+                            if (mine) write_pixel(oy, to_u8(a[0] - b[0]), to_u8(a[1] - b[1]), to_u8(a[2] - b[2]));
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) b[c] = a[c] - uint32_t(kRound);
+                        };
+                        const int sl = e.w & 3;                        // which accumulator row: (oy % 3) + 1
+                        if (sl == 1) finish(va[0], vb[0]);
+                        else if (sl == 2) finish(va[1], vb[1]);
+                        else finish(va[2], vb[2]);
+                    }
+                } else {
+                    tmp[size_t((r - r0) & tmp_mask) * tmp_pitch_w + tid] = out[0] | (out[1] << 8) | (out[2] << 16);
+                }
             }
         }
-        __syncthreads();               // stage consumed (ring slot reusable), intermediate rows visible
+        // Stage consumed: the ring slot may be refilled.  (A per-warp release on an "empty" mbarrier, thread 0 waiting
+        // for it before the refill, was tried instead of this barrier: launches with more CTAs than fit the GPU at
+        // once hung on B200; the barrier costs ~4 % of the warp cycles with three CTAs per SM.)
+        __syncthreads();
         if constexpr (!kVScat) emit_ready(rb);
         if (++buf == p.n_stages) { buf = 0; parity ^= 1u; }
         if (++ibuf == p.n_stages) ibuf = 0;
@@ -598,13 +445,6 @@ resize_generic_kernel(const ResizeParams p, uint32_t n) {
     }
 }
 
-static int pick_bucket(int ksize_h) {
-    const int buckets[] = {3, 5, 9, 13, 17, 25, 33};
-    for (int b : buckets)
-        if (ksize_h <= b) return b;
-    return 0;
-}
-
 static int pick_quads_bucket(int max_taps) {
     const int buckets[] = {4, 8, 12, 16, 20, 28, 36};
     for (int b : buckets)
@@ -612,12 +452,11 @@ static int pick_quads_bucket(int max_taps) {
     return 0;
 }
 
-template <int KSH>
+template <int KQ>
 static cudaError_t set_smem_attr(size_t bytes) {
-    const void *fns[4] = {reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, 0, false>),
-                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, 1, false>),
-                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, 0, true>),
-                          reinterpret_cast<const void *>(resize_bands_kernel<KSH, false, 1, true>)};
+    const void *fns[3] = {reinterpret_cast<const void *>(resize_bands_kernel<KQ, 0>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KQ, 1>),
+                          reinterpret_cast<const void *>(resize_bands_kernel<KQ, 2>)};
     for (const void *fn : fns) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
         if (e != cudaSuccess) return e;
@@ -626,35 +465,20 @@ static cudaError_t set_smem_attr(size_t bytes) {
 }
 
 template <int KQ>
-static cudaError_t set_smem_attr_quads(size_t bytes) {
-    const void *fns[3] = {reinterpret_cast<const void *>(resize_bands_kernel<KQ, false, 2, false>),
-                          reinterpret_cast<const void *>(resize_bands_kernel<KQ, false, 2, true>),
-                          reinterpret_cast<const void *>(resize_bands_kernel<KQ, false, 2, false, true>)};
-    for (const void *fn : fns) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-        if (e != cudaSuccess) return e;
+static void launch_bands(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st, int vmode) {
+    const uint32_t grid = n * uint32_t(p.n_bands);
+    if (vmode == 2) resize_bands_kernel<KQ, 2><<<grid, threads, smem, st>>>(p);
+    else if (vmode == 1) resize_bands_kernel<KQ, 1><<<grid, threads, smem, st>>>(p);
+    else resize_bands_kernel<KQ, 0><<<grid, threads, smem, st>>>(p);
+}
+
+// switch over the tap-capacity buckets
+#define B2_QUADS_DISPATCH(qb, CALL)                                                      \
+    switch (qb) {                                                                        \
+        case 4: CALL(4); break;   case 8: CALL(8); break;   case 12: CALL(12); break;    \
+        case 16: CALL(16); break; case 20: CALL(20); break; case 28: CALL(28); break;    \
+        default: CALL(36); break;                                                        \
     }
-    return cudaSuccess;
-}
-
-template <int KSH>
-static void launch_bands(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st, bool planar,
-                         bool vparam) {
-    const uint32_t grid = n * uint32_t(p.n_bands);
-    if (planar && vparam) resize_bands_kernel<KSH, false, 1, true><<<grid, threads, smem, st>>>(p);
-    else if (planar) resize_bands_kernel<KSH, false, 1, false><<<grid, threads, smem, st>>>(p);
-    else if (vparam) resize_bands_kernel<KSH, false, 0, true><<<grid, threads, smem, st>>>(p);
-    else resize_bands_kernel<KSH, false, 0, false><<<grid, threads, smem, st>>>(p);
-}
-
-template <int KQ>
-static void launch_quads(const ResizeParams &p, uint32_t n, int threads, size_t smem, cudaStream_t st, bool vparam,
-                         bool vscat) {
-    const uint32_t grid = n * uint32_t(p.n_bands);
-    if (vscat) resize_bands_kernel<KQ, false, 2, false, true><<<grid, threads, smem, st>>>(p);
-    else if (vparam) resize_bands_kernel<KQ, false, 2, true><<<grid, threads, smem, st>>>(p);
-    else resize_bands_kernel<KQ, false, 2, false><<<grid, threads, smem, st>>>(p);
-}
 
 }  // namespace b2
 
@@ -679,57 +503,49 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
     B2_CUDA_CHECK(upload(pl->v.coeffs, &pl->d_vcoeffs));
 
     // ---- fast-path geometry -----------------------------------------------------------
-    pl->ksh_bucket = pick_bucket(pl->h.ksize);
     pl->threads = ((out_w + 31) / 32) * 32;
-    if (pl->threads > 256) pl->ksh_bucket = 0;           // thread-per-column layout: out_w <= 256
     {
         int max_taps = 0;
         for (int x = 0; x < out_w; ++x) max_taps = std::max(max_taps, pl->h.bounds[2 * x + 1]);
-        pl->q_bucket = pl->ksh_bucket != 0 ? pick_quads_bucket(max_taps) : 0;
+        pl->q_bucket = pl->threads <= 256 ? pick_quads_bucket(max_taps) : 0;    // thread-per-column layout: out_w <= 256
     }
     const int pitch = in_w * 3;
     pl->tmp_pitch = ((out_w * 4 + 15) / 16) * 16;
     pl->vparam = out_h * (2 + pl->v.ksize) <= kVtabInts;
     if (const char *e = getenv("B2_RESIZE_VPARAM")) pl->vparam = pl->vparam && atoi(e) != 0;
-    // Stage geometry.  The per-stage barrier + refill costs ~80 instructions per thread and stalls the CTA,
-    // so a stage should hold as many rows as fit while TWO CTAs still share an SM (<= 112 KB each):
-    // two stages (the second CTA covers the refill latency), measured best on 1080p at 6 rows per stage
-    // (4.82 ms vs 5.12 ms for 3 x 4 rows; 8 rows drop to one CTA per SM: 6.30 ms).
+    // Stage geometry: two stages per CTA (the other CTAs of the SM cover the refill latency), as many rows per stage
+    // as fit the shared-memory budget.  74 KB = three CTAs (24 warps) per SM: with the scatter-form vertical pass,
+    // 6-row stages at 1080p, measured 3.51 ms per 2 368 images against 3.94 ms for two CTAs with 9-row stages and
+    // 3.51 ms for four CTAs with 4-row stages.
     // Over-read padding per stage = the widest register window + alignment slack.
-    const int overread = 3 * 33 + 64;
+    const int overread = 3 * 36 + 64;
     pl->n_stages = 2;
     if (const char *e = getenv("B2_RESIZE_STAGES")) pl->n_stages = atoi(e) >= 2 && atoi(e) <= kMaxStages ? atoi(e) : 2;
+    size_t budget = 74 * 1024;
+    if (const char *e = getenv("B2_RESIZE_SMEM_KB")) budget = size_t(atoi(e)) * 1024;
+    int rps_cap = 32;
+    if (const char *e = getenv("B2_RESIZE_RPS")) rps_cap = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : rps_cap;
     auto layout = [&](int rps) {
         pl->rows_per_stage = rps;
         pl->stage_bytes = ((rps * pitch + 32 + overread + 127) / 128) * 128;
-        int ring_rows = 8;                                   // rolling intermediate: power of two covering
-        while (ring_rows < 2 * rps + pl->v.ksize + 2) ring_rows <<= 1;   // two stages plus one tap window
+        int ring_rows = 8;                                   // rolling intermediate (thread-private columns): power of
+        while (ring_rows < rps + pl->v.ksize + 2) ring_rows <<= 1;   // two covering one stage plus one tap window
         pl->tmp_ring_rows = ring_rows;
         pl->smem_fixed = size_t(pl->n_stages) * pl->stage_bytes + size_t(ring_rows) * pl->tmp_pitch + 64;
         pl->smem_max = pl->smem_fixed + (pl->vparam ? 0 : size_t(out_h) * (2 + pl->v.ksize) * 4);
     };
-    // Planar IDP.4A pass: rows are whole 48-byte chunks starting 16-byte aligned, and a stage must fit the
-    // register carry of the in-place de-interleave (kPlanarChunks chunks per thread).
-    pl->planar = pl->ksh_bucket != 0 && in_w % 16 == 0 && pl->threads * kPlanarChunks * 48 >= pitch;
-    // pl->planar says the planar pass is POSSIBLE for this shape; which pass a call uses is decided per call
-    // (B2_RESIZE_BESIDE_HASH flag, or B2_RESIZE_PLANAR=0/1 to force one for tests and comparisons).
-    int rps = 32;
-    if (pl->planar && rps > pl->threads * kPlanarChunks * 48 / pitch) rps = pl->threads * kPlanarChunks * 48 / pitch;
+    int rps = rps_cap;
     for (; rps > 1; --rps) {
         layout(rps);
-        if (pl->smem_max <= 112 * 1024) break;
-    }
-    if (const char *e = getenv("B2_RESIZE_RPS")) {                                                         // tuning experiments
-        rps = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : rps;
-        if (rps * pitch > pl->threads * kPlanarChunks * 48) pl->planar = 0;
+        if (pl->smem_max <= budget) break;
     }
     layout(rps);
-    if (pl->smem_max > 220 * 1024) pl->ksh_bucket = 0;       // does not fit at all: generic kernel
+    if (pl->smem_max > 220 * 1024) pl->q_bucket = 0;         // does not fit at all: generic kernel
 
     // ---- scatter-form vertical pass: per input row, the taps of output rows oy_lo .. oy_lo + 2, where oy_lo is the
     // first output row whose window has not ended before this input row.
     pl->scat = 0; pl->d_vscat = nullptr; pl->rps_scat = 0; pl->stage_bytes_scat = 0; pl->smem_scat = 0;
-    if (pl->q_bucket != 0 && pl->ksh_bucket != 0) {
+    if (pl->q_bucket != 0) {
         std::vector<int4> tab(size_t(in_h), make_int4(0, 0, 0, 0));
         bool ok = true;
         int lo = 0;
@@ -752,12 +568,7 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
             tab[r] = make_int4(k[0], k[1], k[2], done ? (lo << 2) | (lo % 3 + 1) : 0);
         }
         if (ok) {
-            int rs = 32;
-            if (const char *e = getenv("B2_RESIZE_RPS")) rs = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : rs;
-            // No intermediate in shared memory, so three CTAs (24 warps) fit an SM with 6-row stages at 1080p: measured
-            // 3.51 ms per 2 368 images against 3.94 ms for two CTAs with 9-row stages; four CTAs (4 rows): 3.51 ms.
-            size_t budget = 74 * 1024;
-            if (const char *e = getenv("B2_RESIZE_SMEM_KB")) budget = size_t(atoi(e)) * 1024;
+            int rs = rps_cap;
             for (; rs >= 1; --rs) {
                 pl->rps_scat = rs;
                 pl->stage_bytes_scat = ((rs * pitch + 32 + overread + 127) / 128) * 128;
@@ -836,7 +647,6 @@ extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint
     }
     p.band_rows = (pl->out_h + n_bands - 1) / n_bands;
     p.n_bands = (pl->out_h + p.band_rows - 1) / p.band_rows;
-    p.max_band_in_rows = 0;
     p.rows_per_stage = pl->rows_per_stage; p.stage_bytes = pl->stage_bytes; p.n_stages = pl->n_stages;
     p.tmp_pitch = pl->tmp_pitch; p.tmp_ring_rows = pl->tmp_ring_rows;
     const size_t smem_launch = pl->smem_fixed + (pl->vparam ? 0 : size_t(p.band_rows) * (2 + pl->v.ksize) * 4);
@@ -852,16 +662,8 @@ extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint
         p.mean[c] = mean ? mean[c] : 0.0f;
         p.inv_std[c] = inv_std ? inv_std[c] : 1.0f;
     }
-    // Horizontal pass: the bands pass (PRMT + IMAD) is the faster one alone; the planar pass (IDP.4A) needs a
-    // third of its ALU work and is the faster one when a hash kernel shares the SMs.
-    bool planar = pl->planar != 0 && (flags & B2_RESIZE_BESIDE_HASH) != 0;
-    if (const char *e = getenv("B2_RESIZE_PLANAR")) planar = pl->planar != 0 && atoi(e) != 0;
-    // The quads pass (IDP.4A on a window de-interleaved in registers) beats both, alone and beside the hash, whenever it
-    // applies; B2_RESIZE_QUADS=0 selects one of the older two (tests and comparisons).
-    bool quads = pl->q_bucket != 0;
-    if (const char *e = getenv("B2_RESIZE_QUADS")) quads = quads && atoi(e) != 0;
-    if (quads) planar = false;
-    const bool fast = pl->ksh_bucket != 0 && resize_path_override() != 1 &&
+    (void)flags;   // B2_RESIZE_BESIDE_HASH is accepted and ignored: one horizontal pass serves both situations now
+    const bool fast = pl->q_bucket != 0 && resize_path_override() != 1 &&
                       uint64_t(n) * uint64_t(p.n_bands) < 0x7fffffffull;
     if (!fast) {
         const uint64_t threads = uint64_t(n) * pl->out_h * pl->out_w;
@@ -870,81 +672,36 @@ extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint
         B2_LAUNCH_CHECK("resize_generic_kernel");
         return B2_OK;
     }
+    // Vertical pass: scatter form for every downscale (B2_RESIZE_VSCAT=0 forces the gather form: tests, comparisons)
+    bool vscat = pl->scat != 0;
+    if (const char *ev = getenv("B2_RESIZE_VSCAT")) vscat = vscat && atoi(ev) != 0;
+    const int vmode = vscat ? 2 : (pl->vparam ? 1 : 0);
+    size_t smem = smem_launch;
+    if (vscat) {
+        p.vscat = pl->d_vscat;
+        p.rows_per_stage = pl->rps_scat; p.stage_bytes = pl->stage_bytes_scat;
+        smem = pl->smem_scat;
+    }
+    const size_t smem_attr = std::max(pl->smem_max, pl->smem_scat);
     static std::mutex mu;
     static size_t attr_bytes[64][8];     // [device][bucket index]: largest smem opt-in done so far
-    static size_t attr_bytes_q[64][8];
-    int bi = 0;
     cudaError_t e = cudaSuccess;
-    if (quads) {
-        bool vscat = pl->scat != 0;
-        if (const char *ev = getenv("B2_RESIZE_VSCAT")) vscat = vscat && atoi(ev) != 0;
-        if (vscat) {
-            p.vscat = pl->d_vscat;
-            p.rows_per_stage = pl->rps_scat; p.stage_bytes = pl->stage_bytes_scat;
-        }
-        const size_t smem_q = vscat ? pl->smem_scat : smem_launch;
-        const size_t smem_attr_q = std::max(pl->smem_max, pl->smem_scat);
-        {
-            std::lock_guard<std::mutex> lock(mu);
-            const int qb = pl->q_bucket;
-            bi = qb <= 20 ? qb / 4 - 1 : (qb == 28 ? 5 : 6);
-            const int dev = pl->device & 63;
-            if (attr_bytes_q[dev][bi] < smem_attr_q) {
-                switch (qb) {
-                    case 4: e = set_smem_attr_quads<4>(smem_attr_q); break;
-                    case 8: e = set_smem_attr_quads<8>(smem_attr_q); break;
-                    case 12: e = set_smem_attr_quads<12>(smem_attr_q); break;
-                    case 16: e = set_smem_attr_quads<16>(smem_attr_q); break;
-                    case 20: e = set_smem_attr_quads<20>(smem_attr_q); break;
-                    case 28: e = set_smem_attr_quads<28>(smem_attr_q); break;
-                    default: e = set_smem_attr_quads<36>(smem_attr_q); break;
-                }
-                if (e == cudaSuccess) attr_bytes_q[dev][bi] = smem_attr_q;
-            }
-        }
-        B2_CUDA_CHECK(e);
-        switch (pl->q_bucket) {
-            case 4: launch_quads<4>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
-            case 8: launch_quads<8>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
-            case 12: launch_quads<12>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
-            case 16: launch_quads<16>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
-            case 20: launch_quads<20>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
-            case 28: launch_quads<28>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
-            default: launch_quads<36>(p, n, pl->threads, smem_q, st, pl->vparam != 0, vscat); break;
-        }
-        B2_LAUNCH_CHECK("resize_bands_kernel<quads>");
-        return B2_OK;
-    }
     {
         std::lock_guard<std::mutex> lock(mu);
-        switch (pl->ksh_bucket) {
-            case 3: bi = 0; break; case 5: bi = 1; break; case 9: bi = 2; break; case 13: bi = 3; break;
-            case 17: bi = 4; break; case 25: bi = 5; break; default: bi = 6; break;
-        }
+        const int qb = pl->q_bucket;
+        const int bi = qb <= 20 ? qb / 4 - 1 : (qb == 28 ? 5 : 6);
         const int dev = pl->device & 63;
-        if (attr_bytes[dev][bi] < pl->smem_max) {
-            switch (pl->ksh_bucket) {
-                case 3: e = set_smem_attr<3>(pl->smem_max); break;
-                case 5: e = set_smem_attr<5>(pl->smem_max); break;
-                case 9: e = set_smem_attr<9>(pl->smem_max); break;
-                case 13: e = set_smem_attr<13>(pl->smem_max); break;
-                case 17: e = set_smem_attr<17>(pl->smem_max); break;
-                case 25: e = set_smem_attr<25>(pl->smem_max); break;
-                default: e = set_smem_attr<33>(pl->smem_max); break;
-            }
-            if (e == cudaSuccess) attr_bytes[dev][bi] = pl->smem_max;
+        if (attr_bytes[dev][bi] < smem_attr) {
+#define B2_CALL(KQ) e = set_smem_attr<KQ>(smem_attr)
+            B2_QUADS_DISPATCH(qb, B2_CALL)
+#undef B2_CALL
+            if (e == cudaSuccess) attr_bytes[dev][bi] = smem_attr;
         }
     }
     B2_CUDA_CHECK(e);
-    switch (pl->ksh_bucket) {
-        case 3: launch_bands<3>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
-        case 5: launch_bands<5>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
-        case 9: launch_bands<9>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
-        case 13: launch_bands<13>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
-        case 17: launch_bands<17>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
-        case 25: launch_bands<25>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
-        default: launch_bands<33>(p, n, pl->threads, smem_launch, st, planar, pl->vparam != 0); break;
-    }
+#define B2_CALL(KQ) launch_bands<KQ>(p, n, pl->threads, smem, st, vmode)
+    B2_QUADS_DISPATCH(pl->q_bucket, B2_CALL)
+#undef B2_CALL
     B2_LAUNCH_CHECK("resize_bands_kernel");
     return B2_OK;
 }

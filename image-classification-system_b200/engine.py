@@ -239,7 +239,9 @@ class ResizePlan:
             out_slot: Optional[torch.Tensor] = None, beside_hash: bool = False):
         """rgb: uint8 device buffer holding n HWC images at byte ``offsets`` (int64[n]).
         Returns (thumb uint8[n,out_h,out_w,3], preview float32[n,3,out_h,out_w] or None).
-        ``beside_hash``: a hash kernel runs on another stream at the same time (B2_RESIZE_BESIDE_HASH)."""
+        ``beside_hash``: a hash kernel runs on another stream at the same time (B2_RESIZE_BESIDE_HASH; kept for
+        callers of the first interface — the kernel now has one horizontal pass that is the faster one in both
+        situations, so the flag changes nothing)."""
         _need_cuda(rgb, offsets, thumb, preview, out_slot)
         init(rgb.device.index)
         n = offsets.numel()

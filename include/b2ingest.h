@@ -112,8 +112,8 @@ int b2_resize_normalize_batch(const b2_resize_plan *plan, const uint8_t *d_rgb,
                               uint8_t *d_thumb, float *d_preview,
                               const float mean[3], const float inv_std[3], void *stream);
 /* Same with flags.  B2_RESIZE_BESIDE_HASH: the caller runs b2_sha256_batch on another stream at the same
- * time; the kernel then uses the horizontal pass that leaves the INT32 ALU pipe to the hash (identical
- * results, slower alone, faster together). */
+ * time.  It used to select a horizontal pass that left the INT32 ALU pipe to the hash; the kernel's single
+ * pass is now the faster one in both situations, so the flag is accepted and changes nothing. */
 #define B2_RESIZE_BESIDE_HASH 1u
 int b2_resize_normalize_batch_ex(const b2_resize_plan *plan, const uint8_t *d_rgb,
                                  const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,

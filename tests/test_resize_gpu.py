@@ -32,18 +32,14 @@ def _drop_plans():
         p.close()
 
 
-@pytest.fixture(params=["auto", "bands", "planar", "quads-gather", "generic"])
+@pytest.fixture(params=["auto", "gather", "generic"])
 def resize_path(request, monkeypatch):
-    """auto = what a plain call gets: the band kernel with the quads horizontal pass (window de-interleaved in
-    registers + IDP.4A) and, for downscales, the scatter-form vertical pass; quads-gather = the same horizontal
-    pass with the gather-form vertical pass (what upscales get); bands = the PRMT + IMAD horizontal pass;
-    planar = the in-place de-interleave + IDP.4A pass wherever the shape allows it;
+    """auto = what a call gets: the band kernel with the scatter-form vertical pass for downscales and the
+    gather-form one for upscales; gather = the band kernel with the gather-form vertical pass forced everywhere;
     generic = the thread-per-output-pixel fallback.  Plans are cached per shape and read some switches when
     they are created, so the cache is emptied around every case."""
     monkeypatch.setenv("B2_RESIZE_PATH", "1" if request.param == "generic" else "0")
-    monkeypatch.setenv("B2_RESIZE_PLANAR", "1" if request.param == "planar" else "0")
-    monkeypatch.setenv("B2_RESIZE_QUADS", "0" if request.param in ("bands", "planar") else "1")
-    monkeypatch.setenv("B2_RESIZE_VSCAT", "0" if request.param == "quads-gather" else "1")
+    monkeypatch.setenv("B2_RESIZE_VSCAT", "0" if request.param == "gather" else "1")
     _drop_plans()
     yield request.param
     _drop_plans()
@@ -85,6 +81,34 @@ def test_non_square_outputs_and_upscale(resize_path):
     _check(imgs, 64, 96)
     _check(imgs, 256, 128)
     _check([synth_image(5, 20, 30)], 256, 256)
+
+
+def test_whole_image_ctas_and_bands_agree(resize_path):
+    """A batch of >= 4 x SM-count images runs one CTA per image (every stage of the ring, every output row through
+    the same three accumulators); a small batch of the same images is cut into bands.  Same pixels either way, and
+    both equal Pillow."""
+    n, H, W = 640, 203, 310
+    g = torch.Generator(device="cuda").manual_seed(77)
+    data = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda", generator=g)
+    off = torch.arange(n, dtype=torch.int64, device="cuda") * (H * W * 3)
+    plan = engine.get_plan(H, W, 48, 64)
+    thumb, prev = plan.run(data.view(-1), off)
+    few, fprev = plan.run(data.view(-1), off[:3].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(thumb[:3], few) and torch.equal(prev[:3], fprev)
+    for i in (0, 1, 317, 639):
+        assert np.array_equal(thumb[i].cpu().numpy(), thumbnail_u8(data[i].cpu().numpy(), 48, 64))
+
+
+@pytest.mark.parametrize("in_shape,out_shape", [((1080, 1919), (256, 256)), ((1081, 1922), (255, 250)),
+                                                ((4320, 7680), (256, 256)), ((700, 4500), (100, 256)),
+                                                ((257, 256), (256, 256)), ((511, 300), (256, 129))])
+def test_odd_widths_and_scales(in_shape, out_shape):
+    """Row pitches that are not multiples of 4 or 16 (every funnel-shift phase, the ragged image tail), scale factors
+    from 1.004 to 30 (tap capacities 4 .. 36 and the generic kernel beyond), non-square outputs."""
+    _drop_plans()
+    _check([synth_image(11, *in_shape)], *out_shape)
+    _drop_plans()
 
 
 def test_structured_images_extremes():

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Time the horizontal passes of resize_bands_kernel (bands / planar / quads) alone and beside the hash.
+"""Time resize_bands_kernel with the gather-form and the scatter-form vertical pass, alone and beside the hash.
 
     python tools/resize_modes.py [n_images]
 
@@ -19,11 +19,11 @@ import torch  # noqa: E402
 import ics_b200  # noqa: E402,F401
 from ics_b200 import engine  # noqa: E402
 
-MODES = {"bands": ("0", "0", "0"), "planar": ("1", "0", "0"), "quads-gather": ("0", "1", "0"), "quads": ("0", "1", "1")}
+MODES = {"gather": "0", "scatter": "1"}
 
 
 def set_mode(name):
-    os.environ["B2_RESIZE_PLANAR"], os.environ["B2_RESIZE_QUADS"], os.environ["B2_RESIZE_VSCAT"] = MODES[name]
+    os.environ["B2_RESIZE_VSCAT"] = MODES[name]
 
 
 def main():

@@ -1,6 +1,5 @@
 #!/usr/bin/env python
-"""Resize throughput over the image shapes of BASELINE configs 1, 3 and 5 (256^2 .. 4096^2, 4K), the three horizontal
-passes (quads = the default), ~6 GB of input per shape, outputs 256x256 u8 + f32."""
+"""Resize throughput over the image shapes of BASELINE configs 1, 3 and 5 (256^2 .. 4096^2, 4K), both vertical passes (scatter = the default for downscales), ~6 GB of input per shape, outputs 256x256 u8 + f32."""
 import os
 import sys
 
@@ -23,8 +22,8 @@ for (H, W) in [(256, 256), (512, 512), (1024, 1024), (1080, 1920), (2048, 2048),
     thumb = torch.empty((n, 256, 256, 3), dtype=torch.uint8, device=dev)
     prev = torch.empty((n, 3, 256, 256), dtype=torch.float32, device=dev)
     out = []
-    for name, (pl_, qd_) in {"quads ": ("0", "1"), "bands ": ("0", "0"), "planar": ("1", "0")}.items():
-        os.environ["B2_RESIZE_PLANAR"], os.environ["B2_RESIZE_QUADS"] = pl_, qd_
+    for name, vs_ in {"scatter": "1", "gather ": "0"}.items():
+        os.environ["B2_RESIZE_VSCAT"] = vs_
         fn = lambda: plan.run(data, off, thumb=thumb, preview=prev)  # noqa: E731
         fn()
         torch.cuda.synchronize()
