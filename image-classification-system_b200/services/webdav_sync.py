@@ -23,12 +23,12 @@ shows the SQLAlchemy adapter).  Listing folders, marking removed images and fold
 """
 from __future__ import annotations
 
-import io
 import logging
 from datetime import datetime, timezone
 from typing import Callable, Dict, List, Optional, Tuple
 
 from .. import hostapi
+from ..feeder import DownloadDecodeFeeder, FeederBatch, image_metadata
 from ..ingest import hash_and_dedupe
 
 logger = logging.getLogger(__name__)
@@ -50,12 +50,18 @@ class WebDAVSync:
     SYNC_METHOD = "webdav"
 
     def __init__(self, nextcloud_client, db, now: Callable[[], datetime] = _utc_now,
-                 batch_size: int = NEXTCLOUD_SYNC_BATCH_SIZE, device: Optional[int] = None):
+                 batch_size: int = NEXTCLOUD_SYNC_BATCH_SIZE, device: Optional[int] = None,
+                 download_workers: int = 1, prefetch_batches: int = 1):
+        """``download_workers`` > 1: ``sync_images_in_folder`` downloads through the feeder (``feeder.py``) —
+        that many GETs in flight and the next ``prefetch_batches`` batches downloading while the current one is
+        hashed and written; 1 = one GET at a time, as the reference does.  Same results either way."""
         self.client = nextcloud_client
         self.db = db
         self._now = now
         self.batch_size = batch_size
         self.device = device
+        self.download_workers = download_workers
+        self.prefetch_batches = prefetch_batches
 
     # ------------------------------------------------------------------ single-item API
     def _calculate_hash_from_bytes(self, data: bytes) -> str:
@@ -71,14 +77,7 @@ class WebDAVSync:
 
     def _get_image_metadata(self, image_data: bytes) -> Dict:
         """Header parse only, in the reference's own host library (Pillow); ``{}`` on any error."""
-        try:
-            from PIL import Image as PILImage
-
-            img = PILImage.open(io.BytesIO(image_data))
-            return {"width": img.width, "height": img.height, "format": img.format, "mode": img.mode}
-        except Exception as e:  # noqa: BLE001 - the reference swallows everything here
-            logger.warning("metadata extraction failed: %s", e)
-            return {}
+        return image_metadata(image_data)
 
     def _fetch(self, image_info: Dict) -> Optional[bytes]:
         """Download into memory; ``None`` on any failure (never aborts the batch)."""
@@ -112,11 +111,14 @@ class WebDAVSync:
             meta["size"] = info.get("content_length", 0)
         return meta
 
-    def _process_image_batch(self, images: List[Dict], folder_path: str, conjunto_id) -> Dict[str, int]:
+    def _process_image_batch(self, images: List[Dict], folder_path: str, conjunto_id,
+                             prefetched: Optional[FeederBatch] = None) -> Dict[str, int]:
+        """``prefetched``: the same images already downloaded (and header-parsed) by the feeder."""
         now = self._now()
-        datas: List[Optional[bytes]] = [
-            self._fetch(info) if self._validate_image(info) else None for info in images
-        ]
+        if prefetched is not None:
+            datas: List[Optional[bytes]] = prefetched.datas
+        else:
+            datas = [self._fetch(info) if self._validate_image(info) else None for info in images]
         try:
             decision = hash_and_dedupe(datas, existing_hashes=lambda hs: self.db.get_many(hs).keys(),
                                        device=self.device)
@@ -138,7 +140,7 @@ class WebDAVSync:
                         "nextcloud": {"file_id": nc["file_id"], "etag": nc["etag"],
                                       "content_type": nc["content_type"], "size": nc["size"],
                                       "last_modified": nc["last_modified"]},
-                        "image": self._get_image_metadata(datas[i]),
+                        "image": prefetched.metadata[i] if prefetched is not None else self._get_image_metadata(datas[i]),
                         "sync": {"sync_method": self.SYNC_METHOD, "sync_timestamp": now.isoformat()},
                     },
                     "existe_no_nextcloud": True,
@@ -171,8 +173,14 @@ class WebDAVSync:
         try:
             items = self.client.list_folder(folder_path, depth=1)
             images = self.client.filter_images(items)
-            for i in range(0, len(images), self.batch_size):
-                b = self._process_image_batch(images[i:i + self.batch_size], folder_path, conjunto_id)
+            if self.download_workers > 1:
+                feeder = DownloadDecodeFeeder(self._fetch, self._validate_image, self.batch_size,
+                                              self.download_workers, prefetch_batches=self.prefetch_batches)
+                batches = ((fb.infos, fb) for fb in feeder.batches(images))
+            else:
+                batches = ((images[i:i + self.batch_size], None) for i in range(0, len(images), self.batch_size))
+            for infos, fb in batches:
+                b = self._process_image_batch(infos, folder_path, conjunto_id, prefetched=fb)
                 stats["images_processed"] += b["processed"]
                 stats["images_created"] += b["created"]
                 stats["images_updated"] += b["updated"]

@@ -90,3 +90,59 @@ def test_buscar_imagens_por_hash_replay(ref_ingest):
     assert buscar_imagens_por_hash(ups, DictImageStore(rows)) == ref_ingest["upload_lookup"]["response"]
     with pytest.raises(NoFilesError):
         buscar_imagens_por_hash([], DictImageStore(rows))
+
+
+def test_sync_with_feeder_equals_sequential_sync(ref_ingest):
+    """Eight GETs in flight and the next batch downloading while the current one is hashed (feeder.py, SURVEY 8(f)
+    rank 4): same stats, same rows, same commits as the one-GET-at-a-time loop."""
+    def run(workers):
+        files, infos, client = ingest_scenario(ref_ingest)
+        client.list_folder = lambda folder, depth=1: infos * 6
+        store = DictImageStore()
+        stats = WebDAVSync(client, store, now=_Clock(), batch_size=20, download_workers=workers) \
+            .sync_images_in_folder("/set1", "cid")
+        return stats, dump_rows(store.rows), store.commits
+
+    s1, rows1, c1 = run(1)
+    s8, rows8, c8 = run(8)
+    assert s1 == s8 and c1 == c8 and set(rows1) == set(rows8)
+    for h in rows1:
+        for key in KEYS:
+            assert rows1[h][key] == rows8[h][key], (h, key)
+
+
+def test_feeder_to_ingest_batch_thumbnails():
+    """Listing -> feeder (download + Pillow decode on worker threads) -> ingest_batch: hashes of the FILE bytes,
+    thumbnails of the DECODED pixels — the two buffers the real service has (production note)."""
+    import hashlib
+    import io
+
+    import numpy as np
+    from PIL import Image
+
+    from ics_b200.feeder import DownloadDecodeFeeder
+    from ics_b200.ingest import ingest_batch
+    from oracle import thumbnail_u8
+
+    rng = np.random.default_rng(5)
+    files, pixels = {}, {}
+    for i, (h, w) in enumerate([(300, 400), (300, 400), (64, 48), (531, 257), (300, 400)]):
+        arr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if i != 1 else pixels["f0.png"]
+        buf = io.BytesIO()
+        Image.fromarray(arr, "RGB").save(buf, "PNG")
+        files[f"f{i}.png"], pixels[f"f{i}.png"] = buf.getvalue(), arr
+    files["f5.png"] = b"\x89PNG but truncated"
+    infos = [{"name": k, "path": "/s/" + k} for k in files]
+    feeder = DownloadDecodeFeeder(lambda info: files[info["name"]], batch_size=4, download_workers=4, decode=True)
+    known = set()
+    for b in feeder.batches(infos):
+        res = ingest_batch(b.datas, decoded_rgb=b.rgb, existing_hashes=known, out_h=64, out_w=64)
+        for j, info in enumerate(b.infos):
+            assert res.decision.hashes[j] == hashlib.sha256(files[info["name"]]).hexdigest()
+            if b.rgb[j] is not None:
+                assert np.array_equal(res.thumbs[j], thumbnail_u8(pixels[info["name"]], 64, 64))
+            else:
+                assert info["name"] == "f5.png" and not res.thumbs[j].any()
+        known |= {h for h in res.decision.hashes if h}
+    # f1 is a byte copy of f0: same PNG bytes -> second occurrence is an update, not a create
+    assert len(known) == 5
