@@ -137,3 +137,26 @@ def test_device_batch_full_size_properties():
     for i in (0, 3, 63):
         want = thumbnail_u8(data[i].cpu().numpy(), 256, 256)
         assert np.array_equal(thumb[i].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("h,w,oh,ow,n,pad", [(90, 160, 32, 32, 3, 0), (45, 67, 16, 24, 600, 0), (45, 67, 16, 24, 5, 7),
+                                            (45, 67, 16, 24, 600, 13), (20, 30, 64, 48, 4, 3), (90, 2000, 16, 40, 2, 1)])
+def test_image_offsets_any_alignment(h, w, oh, ow, n, pad, resize_path):
+    """Images packed back to back at arbitrary byte offsets (pad != 0: no image starts 16-byte aligned, so the band
+    kernel takes its cooperative-copy path instead of the bulk copy); bands and whole-image CTAs; first and last
+    image against Pillow."""
+    from PIL import Image
+    g = torch.Generator(device="cuda").manual_seed(9)
+    L = h * w * 3
+    stride = L + pad
+    data = torch.randint(0, 256, (n * stride + 64,), dtype=torch.uint8, device="cuda", generator=g)
+    off = torch.arange(n, dtype=torch.int64, device="cuda") * stride + (1 if pad else 0)
+    plan = engine.get_plan(h, w, oh, ow)
+    thumb, prev = plan.run(data, off)
+    torch.cuda.synchronize()
+    for i in (0, n // 2, n - 1):
+        o = int(off[i])
+        img = data[o:o + L].cpu().numpy().reshape(h, w, 3)
+        want = np.asarray(Image.fromarray(img, "RGB").resize((ow, oh), Image.BILINEAR))
+        assert np.array_equal(thumb[i].cpu().numpy(), want), i
+        np.testing.assert_allclose(prev[i].cpu().numpy(), preview_f32(want, (0, 0, 0), (1, 1, 1)), rtol=F32_RTOL, atol=1e-7)
