@@ -110,3 +110,83 @@ class IngestPipeline:
                               {"processed": c[0], "created": c[1], "updated": c[2]},
                               self.h_thumbs[:n], self.h_prev[:n] if self.h_prev is not None else None,
                               int(h2d.value), int(d2h.value), self.h_first[:n], self.h_last[:n])
+
+
+@dataclass
+class MixedResult:
+    digests: "np.ndarray"                 # uint8 [n, 32], listing order
+    is_new: "np.ndarray"                  # uint8 [n]
+    first_index: "np.ndarray"             # int32 [n]: first occurrence of the same content in the listing
+    last_index: "np.ndarray"
+    stats: Dict[str, int]
+    thumbs: "np.ndarray"                  # uint8 [n, out_h, out_w, 3], listing order
+    previews: Optional["np.ndarray"]
+    h2d_bytes: int
+    d2h_bytes: int
+
+
+class MixedShapeIngest:
+    """Streaming ingest of a listing whose images have different shapes (BASELINE config 3).
+
+    The native stream (``b2_ingest_stream_*``) is fixed-shape, so a listing is split by shape: one
+    :class:`IngestPipeline` per shape class, all submitted before any is waited for (their copies and kernels
+    share the GPU), and ONE dedupe over the digests of the whole listing in listing order afterwards
+    (``b2_dedupe_host``) — two files of equal byte length can be byte-identical whatever their shapes, and the
+    first-seen / last-seen rule of ``webdav_sync.py:324-398`` is about listing order, not shape order.
+
+    ``run(groups)``: ``groups[(h, w)] = (images, positions)`` with ``images`` a uint8 host tensor
+    ``[n_s, h*w*3]`` (page-locked for full-speed copies) and ``positions`` the listing index of each of them
+    (int array, all groups together a permutation of ``0..n-1``).  As for the native stream, ``h*w*3`` must be a
+    multiple of 16 (images are packed back to back and copied in 16-byte units); other shapes go through the blocking
+    ``hostapi.sha256_host`` + ``hostapi.thumbnails``.
+    """
+
+    def __init__(self, capacity: Dict, chunk_bytes: int = 1 << 30, out_h: int = 256, out_w: int = 256,
+                 want_preview: bool = True, device: Optional[int] = None):
+        """``capacity[(h, w)]`` = most images of that shape in one listing (device staging is sized by it)."""
+        self.out_h, self.out_w, self.want_preview = out_h, out_w, want_preview
+        self.device = engine.init(device)
+        self.pipes: Dict = {}
+        for (h, w), cap in capacity.items():
+            chunk = max(1, min(cap, chunk_bytes // (h * w * 3)))
+            self.pipes[(h, w)] = IngestPipeline(h, w, cap, chunk_images=chunk, out_h=out_h, out_w=out_w,
+                                                want_preview=want_preview, device=self.device)
+
+    def close(self) -> None:
+        for p in self.pipes.values():
+            p.close()
+        self.pipes = {}
+
+    def run(self, groups: Dict, existing_sorted=None) -> MixedResult:
+        import numpy as np
+
+        from . import hostapi
+
+        n = sum(int(imgs.shape[0]) for imgs, _ in groups.values())
+        # biggest images first: their hash latency (one lane, ~48 MB/s) is the tail everything else hides under
+        order = sorted(groups, key=lambda s: -s[0] * s[1])
+        for shape in order:
+            self.pipes[shape].submit(groups[shape][0])
+        digests = np.zeros((n, 32), dtype=np.uint8)
+        thumbs = np.zeros((n, self.out_h, self.out_w, 3), dtype=np.uint8)
+        previews = np.zeros((n, 3, self.out_h, self.out_w), dtype=np.float32) if self.want_preview else None
+        seen = np.zeros(n, dtype=bool)
+        h2d = d2h = 0
+        for shape in order:
+            res = self.pipes[shape].result()
+            pos = np.asarray(groups[shape][1], dtype=np.int64)
+            assert pos.shape[0] == res.digests.shape[0] and not seen[pos].any(), "positions must be a permutation"
+            seen[pos] = True
+            digests[pos] = res.digests.numpy()
+            thumbs[pos] = res.thumbs.numpy()
+            if previews is not None:
+                previews[pos] = res.previews.numpy()
+            h2d += res.h2d_bytes
+            d2h += res.d2h_bytes
+        assert seen.all(), "positions must cover the listing"
+        ex = None
+        if existing_sorted is not None and len(existing_sorted):
+            ex = np.ascontiguousarray(np.asarray(existing_sorted, dtype=np.uint8)).reshape(-1, 32)
+        is_new, first, last, c = hostapi.dedupe_host(digests, None, ex, self.device)
+        return MixedResult(digests, is_new, first, last, {"processed": c[0], "created": c[1], "updated": c[2]},
+                           thumbs, previews, h2d, d2h)

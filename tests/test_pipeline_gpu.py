@@ -153,3 +153,46 @@ def test_config5_4k_duplicates_thumbnails_tally():
     img, cls, act = synth_label_rows(nu, 50, 100)
     t = ics_b200.label_tally(img, cls, act, nu, 50)
     assert np.array_equal(t.counts, label_tally(img, cls, act, nu, 50))
+
+
+def test_mixed_shape_listing_streams_per_shape_and_dedupes_across_shapes():
+    """BASELINE config 3 in miniature: a listing of three shapes, two of equal byte length (so byte-identical files of
+    different shapes exist), duplicates inside and across shape classes, one stored digest.  Digests == hashlib,
+    thumbnails == Pillow, dedupe == the sequential loop of webdav_sync.py:311-400 over the listing."""
+    import hashlib
+
+    from PIL import Image
+
+    from ics_b200.hostapi import sort_digests
+    from ics_b200.pipeline import MixedShapeIngest
+
+    rng = np.random.default_rng(33)
+    shapes = [(64, 256), (128, 128), (96, 72)]                        # 64x256 and 128x128: same byte length
+    listing = []
+    for i in range(17):
+        h, w = shapes[i % 3]
+        listing.append(((h, w), rng.integers(0, 256, h * w * 3, dtype=np.uint8)))
+    listing[7] = ((128, 128), listing[0][1].copy())                   # same bytes as listing[0], other shape
+    listing[9] = (listing[3][0], listing[3][1].copy())                # same bytes, same shape
+    listing[16] = ((64, 256), listing[1][1].copy())                   # same bytes as listing[1], other shape
+    stored = hashlib.sha256(listing[5][1].tobytes()).digest()
+    groups = {}
+    for s in shapes:
+        pos = [i for i, (sh, _) in enumerate(listing) if sh == s]
+        groups[s] = (_pinned(np.stack([listing[i][1] for i in pos])), pos)
+    mixed = MixedShapeIngest({s: 8 for s in shapes}, chunk_bytes=3 * 64 * 256 * 3, out_h=32, out_w=48)
+    table = sort_digests(np.frombuffer(stored, dtype=np.uint8).reshape(1, 32))
+    for _ in range(2):                                                # reusable
+        res = mixed.run(groups, table)
+    mixed.close()
+    seen, created = {stored}, 0
+    for i, ((h, w), buf) in enumerate(listing):
+        d = hashlib.sha256(buf.tobytes()).digest()
+        assert bytes(res.digests[i]) == d
+        assert bool(res.is_new[i]) == (d not in seen)
+        created += d not in seen
+        seen.add(d)
+        want = np.asarray(Image.fromarray(buf.reshape(h, w, 3), "RGB").resize((48, 32), Image.BILINEAR))
+        assert np.array_equal(res.thumbs[i], want)
+    assert res.stats == {"processed": 17, "created": created, "updated": 17 - created} and created == 13
+    assert res.first_index[7] == 0 and res.last_index[0] == 7 and res.first_index[16] == 1
