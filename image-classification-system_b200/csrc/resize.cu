@@ -393,9 +393,8 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
                 }
             }
         }
-        // Stage consumed: the ring slot may be refilled.  (A per-warp release on an "empty" mbarrier, thread 0 waiting
-        // for it before the refill, was tried instead of this barrier: launches with more CTAs than fit the GPU at
-        // once hung on B200; the barrier costs ~4 % of the warp cycles with three CTAs per SM.)
+        // Stage consumed: the ring slot may be refilled.  (Per-warp releases on an "empty" mbarrier with a dedicated
+        // producer warp were measured instead of this barrier: 3.55 ms against 3.34 ms, profiles/r1_resize_notes.md.)
         __syncthreads();
         if constexpr (!kVScat) emit_ready(rb);
         if (++buf == p.n_stages) { buf = 0; parity ^= 1u; }
