@@ -114,15 +114,28 @@ class IngestPipeline:
 
 @dataclass
 class MixedResult:
+    """Digests and dedupe decisions are in listing order.  Thumbnails and previews stay where the per-shape streams
+    put them (page-locked, one block per shape class: scattering ~1 MB per image into listing order costs more host
+    time than the GPU needs for the images); ``thumb(i)`` / ``preview(i)`` address them by listing position."""
     digests: "np.ndarray"                 # uint8 [n, 32], listing order
     is_new: "np.ndarray"                  # uint8 [n]
     first_index: "np.ndarray"             # int32 [n]: first occurrence of the same content in the listing
     last_index: "np.ndarray"
     stats: Dict[str, int]
-    thumbs: "np.ndarray"                  # uint8 [n, out_h, out_w, 3], listing order
-    previews: Optional["np.ndarray"]
+    thumbs_by_shape: Dict                 # (h, w) -> uint8 [n_s, out_h, out_w, 3]
+    previews_by_shape: Optional[Dict]     # (h, w) -> float32 [n_s, 3, out_h, out_w]
+    where: "np.ndarray"                   # int32 [n, 2]: (index of the shape class in `shapes`, row inside its block)
+    shapes: list
     h2d_bytes: int
     d2h_bytes: int
+
+    def thumb(self, i: int):
+        k, j = self.where[i]
+        return self.thumbs_by_shape[self.shapes[k]][j]
+
+    def preview(self, i: int):
+        k, j = self.where[i]
+        return None if self.previews_by_shape is None else self.previews_by_shape[self.shapes[k]][j]
 
 
 class MixedShapeIngest:
@@ -180,19 +193,21 @@ class MixedShapeIngest:
         groups, order = self._groups, self._order
         n = sum(int(imgs.shape[0]) for imgs, _ in groups.values())
         digests = np.zeros((n, 32), dtype=np.uint8)
-        thumbs = np.zeros((n, self.out_h, self.out_w, 3), dtype=np.uint8)
-        previews = np.zeros((n, 3, self.out_h, self.out_w), dtype=np.float32) if self.want_preview else None
+        where = np.zeros((n, 2), dtype=np.int32)
+        thumbs, previews = {}, ({} if self.want_preview else None)
         seen = np.zeros(n, dtype=bool)
         h2d = d2h = 0
-        for shape in order:
+        for k, shape in enumerate(order):
             res = self.pipes[shape].result()
             pos = np.asarray(groups[shape][1], dtype=np.int64)
             assert pos.shape[0] == res.digests.shape[0] and not seen[pos].any(), "positions must be a permutation"
             seen[pos] = True
             digests[pos] = res.digests.numpy()
-            thumbs[pos] = res.thumbs.numpy()
-            if previews is not None:
-                previews[pos] = res.previews.numpy()
+            where[pos, 0] = k
+            where[pos, 1] = np.arange(pos.shape[0], dtype=np.int32)
+            thumbs[shape] = res.thumbs.numpy()              # views of the pipeline's page-locked buffers: valid until
+            if previews is not None:                        # the next submit() on this object
+                previews[shape] = res.previews.numpy()
             h2d += res.h2d_bytes
             d2h += res.d2h_bytes
         assert seen.all(), "positions must cover the listing"
@@ -202,4 +217,4 @@ class MixedShapeIngest:
             ex = np.ascontiguousarray(np.asarray(existing_sorted, dtype=np.uint8)).reshape(-1, 32)
         is_new, first, last, c = hostapi.dedupe_host(digests, None, ex, self.device)
         return MixedResult(digests, is_new, first, last, {"processed": c[0], "created": c[1], "updated": c[2]},
-                           thumbs, previews, h2d, d2h)
+                           thumbs, previews, where, list(order), h2d, d2h)

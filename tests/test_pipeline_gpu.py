@@ -193,6 +193,7 @@ def test_mixed_shape_listing_streams_per_shape_and_dedupes_across_shapes():
         created += d not in seen
         seen.add(d)
         want = np.asarray(Image.fromarray(buf.reshape(h, w, 3), "RGB").resize((48, 32), Image.BILINEAR))
-        assert np.array_equal(res.thumbs[i], want)
+        assert np.array_equal(res.thumb(i), want)
+        np.testing.assert_allclose(res.preview(i), preview_f32(want, (0, 0, 0), (1, 1, 1)), rtol=1e-5, atol=1e-7)
     assert res.stats == {"processed": 17, "created": created, "updated": 17 - created} and created == 13
     assert res.first_index[7] == 0 and res.last_index[0] == 7 and res.first_index[16] == 1
