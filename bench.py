@@ -491,6 +491,17 @@ def run_graft(args):
             return {"bound": "int32 ALU pipe", "achieved": achieved, "peak": peak, "unit": "G warp-instructions/s",
                     "frac": achieved / peak, "alu_instructions_per_64B_block": 1290}
 
+        def lone_warp_issue_roofline(bytes_, ms, clk, warps):
+            # With one resident warp per SM sub-partition (all the 1080p images that fit HBM allow) the hash is bound by
+            # the rate at which ONE warp can issue: a 32-thread instruction takes two clocks to dispatch whatever pipe it
+            # goes to, so 1 416 instructions per 64-byte block cost 2 832 clocks per block and warp.
+            sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+            achieved = bytes_ / 64.0 / 32.0 * 1416.0 / (ms / 1e3) / 1e9
+            peak = warps * 0.5 * sm_mhz * 1e6 / 1e9
+            return {"bound": "issue rate of a lone warp (1 instruction / 2 clocks)", "achieved": achieved, "peak": peak,
+                    "unit": "G warp-instructions/s", "frac": achieved / peak, "instructions_per_64B_block": 1416,
+                    "resident_warps": warps}
+
         cores = os.cpu_count() or 1
         cpu_n = 512 * cores                                    # ~10-15 s of work on every core
         cpu_v, cpu_dt = cpu_ingest_sample(cpu_n, cores)
@@ -512,7 +523,8 @@ def run_graft(args):
                              note="dominant kernel of the ingest step (79 % of it); sha256 is bound by the INT32 ALU pipe "
                                   "(1 290 ALU instructions per 64-byte block, pipe 90 % busy under ncu), not by HBM: "
                                   "frac of HBM peak is reported for reference, the HBM-bound kernels are under `kernels`"),
-                             int_alu=int_alu_roofline(sha_bytes, ms_sha, clocks)),
+                             int_alu=int_alu_roofline(sha_bytes, ms_sha, clocks),
+                             lone_warp_issue=lone_warp_issue_roofline(sha_bytes, ms_sha, clocks, (n_img + 31) // 32)),
             "kernels": {
                 "sha256_lanes_kernel": roof(sha_bytes, ms_sha, "sha256_lanes_kernel"),
                 "resize_bands_kernel": roof(resize_bytes, ms_resize, "resize_bands_kernel",
