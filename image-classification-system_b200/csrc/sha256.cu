@@ -209,6 +209,124 @@ sha256_lanes_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict
     sha256_store_digest(s, digests + 32ull * msg);
 }
 
+// ----------------------------------------------------------------------------------------
+// Path 2: a warp PAIR per 32 messages, for batches that leave SM sub-partitions idle.
+// One lane hashes ~45 MB/s whatever the batch holds (a lone warp issues one instruction every two clocks and a
+// block costs 1 416 of them), so a few large messages take as long as a GPU full of them.  Here the block's work
+// is split across two warps that the hardware places on different sub-partitions: warp 0 loads the message,
+// byte-swaps it, expands the message schedule and writes W[t] + K[t] for the 64 rounds into shared memory
+// (16 STS.128 per block, ~600 instructions); warp 1 reads them (16 LDS.128) and runs the rounds (~990
+// instructions) — the longer half, so a message moves ~1.4x faster.  Two block buffers, handed over with the
+// named-barrier producer / consumer pattern (bar.arrive by the side that is done, bar.sync by the side that
+// waits; 64 participants).  Lanes of a warp can have different lengths: both warps loop to the longest one.
+// Only worth it while message warps x 2 fit the sub-partitions (b2_sha256_batch decides).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" :: "r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(64)
+sha256_pair_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ offsets,
+                   const uint64_t *__restrict__ lengths, const uint32_t *__restrict__ order,
+                   uint32_t n, uint8_t *__restrict__ digests) {
+    __shared__ __align__(16) uint4 wk[2][16 * 32];           // [buffer][quad of rounds][lane]: W[t] + K[t], t = 4q .. 4q+3
+    const uint32_t lane = threadIdx.x & 31;
+    const bool rounds_warp = threadIdx.x >= 32;
+    const uint32_t slot = blockIdx.x * 32 + lane;
+    const bool live = slot < n;
+    const uint32_t msg = live ? (order ? order[slot] : slot) : 0u;
+    const uint8_t *p = data + (live ? offsets[msg] : 0ull);
+    const uint64_t len = live ? lengths[msg] : 0ull;
+    const uint64_t nfull64 = len >> 6;
+    const uint32_t nfull = nfull64 > 0xffffffffull ? 0xffffffffu : uint32_t(nfull64);   // < 256 GiB per message
+    const uint32_t nmax = __reduce_max_sync(0xffffffffu, nfull);
+    constexpr int kFull = 1, kEmpty = 3;                      // named barriers 1, 2 (full) and 3, 4 (empty); 0 = __syncthreads
+
+    if (!rounds_warp) {
+        // ---- schedule warp
+        const bool al = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+        const uint4 *q = reinterpret_cast<const uint4 *>(p);
+        uint4 cur[4] = {}, nxt[4] = {};
+        if (al && nfull > 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[i] = __ldg(q + i);
+        }
+        for (uint32_t blk = 0; blk < nmax; ++blk) {
+            const int buf = blk & 1;
+            if (blk >= 2) named_bar_sync(kEmpty + buf);       // the rounds warp has read this buffer's previous block
+            if (blk < nfull) {
+                uint32_t w[16];
+                if (al) {
+                    // This warp needs ~1 200 clocks per block, less than a trip to HBM: besides the register prefetch of
+                    // the next block, pull the line 8 blocks ahead into L2 (one prefetch per 128-byte line).
+                    if ((blk & 1) == 0 && blk + 8 < nfull)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(q + 4 * (uint64_t(blk) + 8)));
+                    if (blk + 1 < nfull) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) nxt[i] = __ldg(q + 4 * (uint64_t(blk) + 1) + i);
+                    }
+                    words_from_v4(w, cur);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+                } else {                                      // unaligned start: byte loads (correct, slower)
+                    const uint8_t *b = p + (uint64_t(blk) << 6);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        w[j] = (uint32_t(b[4 * j]) << 24) | (uint32_t(b[4 * j + 1]) << 16) |
+                               (uint32_t(b[4 * j + 2]) << 8) | uint32_t(b[4 * j + 3]);
+                }
+                uint4 *dst = &wk[buf][lane];
+#pragma unroll
+                for (int t4 = 0; t4 < 16; ++t4) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = 4 * t4 + u;
+                        if (t >= 16)
+                            w[t & 15] = w[t & 15] + B2_SSIG0(w[(t + 1) & 15]) + w[(t + 9) & 15] + B2_SSIG1(w[(t + 14) & 15]);
+                        o[u] = w[t & 15] + kK[t];
+                    }
+                    dst[t4 * 32] = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            named_bar_arrive(kFull + buf);
+        }
+        return;
+    }
+
+    // ---- rounds warp
+    Sha256State s;
+    s.init();
+    for (uint32_t blk = 0; blk < nmax; ++blk) {
+        const int buf = blk & 1;
+        named_bar_sync(kFull + buf);
+        if (blk < nfull) {
+            const uint4 *src = &wk[buf][lane];
+            uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3];
+            uint32_t e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+#pragma unroll
+            for (int t4 = 0; t4 < 16; ++t4) {
+                const uint4 x = src[t4 * 32];
+                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t hkw = h + xs[u];
+                    const uint32_t t1 = B2_BSIG1(e) + B2_CH(e, f, g) + hkw;
+                    const uint32_t t2 = B2_BSIG0(a) + B2_MAJ(a, b, c);
+                    h = g; g = f; f = e; e = d + t1;
+                    d = c; c = b; b = a; a = t1 + t2;
+                }
+            }
+            s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d;
+            s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+        }
+        if (blk + 2 < nmax) named_bar_arrive(kEmpty + buf);   // only when the schedule warp will wait for it
+    }
+    if (!live) return;
+    const uint8_t *tail = p + (nfull64 << 6);
+    sha256_finish(s, [&](uint32_t i) -> uint32_t { return tail[i]; }, static_cast<uint32_t>(len & 63), len);
+    sha256_store_digest(s, digests + 32ull * msg);
+}
+
 __global__ void digest_hex_kernel(const uint8_t *__restrict__ digests, uint32_t n, char *__restrict__ hex) {
     // one thread per digest byte-pair word: thread t handles 4 digest bytes -> 8 hex chars
     const uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
@@ -258,13 +376,25 @@ extern "C" int b2_sha256_batch(const uint8_t *d_data, const uint64_t *d_offsets,
     // Ask for the shared-memory-heavy L1 split, like the resize kernel: an SM only changes its carve-out
     // when it is idle, so kernels with different preferences never share an SM and a hash launched beside
     // a resize on another stream would simply wait for it (measured: no overlap at all without this).
-    static std::once_flag carve_once[64];                    // function attributes are per device
+    static std::once_flag carve_once[64], pair_once[64];     // function attributes are per device
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     std::call_once(carve_once[cur_dev & 63], [] {
         cudaFuncSetAttribute(sha256_lanes_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(sha256_lanes_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     });
+    // Few message warps: the warp-pair kernel (two sub-partitions per 32 messages, ~1.4x the per-message speed).
+    // B2_SHA_PAIR = 0 / 1 forces the choice (tests, comparisons).
+    bool pair = warps * 2u <= uint32_t(sm_count()) * 4u;
+    if (const char *e = getenv("B2_SHA_PAIR")) pair = atoi(e) != 0;
+    if (pair) {
+        std::call_once(pair_once[cur_dev & 63], [] {
+            cudaFuncSetAttribute(sha256_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        });
+        sha256_pair_kernel<<<warps, 64, 0, st>>>(d_data, d_offsets, d_lengths, d_order, n, d_digests);
+        B2_LAUNCH_CHECK("sha256_pair_kernel");
+        return B2_OK;
+    }
     int variant = sha_variant_override();
     if (variant < 0) variant = warps > uint32_t(sm_count()) * 4u ? 2 : 0;    // more than one warp per sub-partition
     if (variant == 0)

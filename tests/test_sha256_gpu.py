@@ -15,11 +15,13 @@ from oracle import sha256_hex, synth_image
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["iadd3", "imad"])
+@pytest.fixture(params=["iadd3", "imad", "pair"])
 def sha_path(request, monkeypatch):
-    """Both code variants of the compression function: adds as ptxas schedules them (what one warp per
-    sub-partition gets) and two-input adds on the FMA pipe (what larger batches get)."""
-    monkeypatch.setenv("B2_SHA_VARIANT", {"iadd3": "0", "imad": "2"}[request.param])
+    """The three kernels: one lane per message with the adds as ptxas schedules them (what one warp per
+    sub-partition gets) or with two-input adds on the FMA pipe (what larger batches get), and the warp-pair
+    kernel (schedule warp + rounds warp per 32 messages; what batches that leave sub-partitions idle get)."""
+    monkeypatch.setenv("B2_SHA_PAIR", "1" if request.param == "pair" else "0")
+    monkeypatch.setenv("B2_SHA_VARIANT", {"iadd3": "0", "imad": "2", "pair": "0"}[request.param])
     return request.param
 
 
