@@ -8,7 +8,8 @@
 // messages: one lane owns one message and runs the 64-round compression in registers; a
 // warp owns 32 messages (sorted by length by the caller so lanes finish together).  The
 // kernel is bound by the INT32 ALU pipe (~1400 LOP3/SHF/IADD3 per 64-byte block), not by
-// HBM — see DESIGN.md "sha256_lanes".
+// HBM — see DESIGN.md "sha256_lanes".  Batches that leave SM sub-partitions idle run as warp
+// pairs instead (sha256_pair_kernel, Path 2 below).
 //
 // sha256_lanes_kernel: each lane streams its own message with 128-bit loads (four per 64-byte block,
 // prefetched one block ahead).  Every 32-byte sector fetched is fully used, so DRAM traffic = message bytes
