@@ -45,6 +45,8 @@ from .resize import (  # noqa: F401
     preview_f32,
     resample_restated,
     precompute_coeffs,
+    scatter_table,
+    kernel_model,
 )
 from .labels import (  # noqa: F401
     label_tally,

@@ -121,3 +121,80 @@ def resample_restated(rgb_hwc: np.ndarray, out_h: int = 256, out_w: int = 256) -
             out[y] = _clip8(acc)
         src = out
     return np.ascontiguousarray(src)
+
+
+# ---------------------------------------------------------------------------------------------
+# Model of the CUDA band kernel's arithmetic (csrc/resize.cu), so that the two reformulations it
+# relies on are checked on the CPU too, over many more shapes than the GPU tests visit:
+#   * horizontal pass: a 22-bit tap as three 8-bit limbs, one unsigned dot product per limb
+#     (IDP.4A), recombined as s0 + (s1 << 8) + (s2 << 16) in uint32, NO clip;
+#   * vertical pass in scatter form: per INPUT row the taps of the <= 3 output rows whose
+#     windows cover it; output row oy accumulates in slot oy % 3; the uint32 accumulators are
+#     never reset — they run on modulo 2^32 and a second value remembers where the row started.
+# ---------------------------------------------------------------------------------------------
+def scatter_table(in_size: int, out_size: int):
+    """``(table int64[in_size, 4], eligible)`` — the table ``b2_resize_plan_create`` builds for
+    ``kVMode == 2``: columns 0..2 = tap of the output row living in accumulator 0, 1, 2 for this
+    input row (0 when none), column 3 = ``(oy << 2) | (oy % 3 + 1)`` of the output row that ENDS
+    with this input row, else 0.  ``eligible`` is False when the plan must use the gather form:
+    windows not monotone, more than three output rows over one input row, or a negative tap."""
+    bounds, kk, _ = precompute_coeffs(in_size, out_size)
+    first = bounds[:, 0].astype(np.int64)
+    last = first + bounds[:, 1].astype(np.int64) - 1
+    table = np.zeros((in_size, 4), dtype=np.int64)
+    ok = bool(np.all(first[:-1] <= first[1:]) and np.all(last[:-1] < last[1:])) if out_size > 1 else True
+    lo = 0
+    for r in range(in_size):
+        while lo < out_size and last[lo] < r:
+            lo += 1
+        for j in range(3):
+            oy = lo + j
+            if oy < out_size and first[oy] <= r <= last[oy]:
+                c = int(kk[oy, r - first[oy]])
+                ok = ok and c >= 0
+                table[r, oy % 3] = c
+        if lo + 3 < out_size and first[lo + 3] <= r:
+            ok = False
+        if lo < out_size and last[lo] == r:
+            table[r, 3] = (lo << 2) | (lo % 3 + 1)
+    return table, ok
+
+
+def kernel_model(rgb_hwc: np.ndarray, out_h: int, out_w: int):
+    """What ``resize_bands_kernel<KQ, 2>`` computes, in its own arithmetic; ``None`` when the
+    scatter form does not apply to this vertical geometry (the kernel then gathers)."""
+    in_h, in_w, _ = rgb_hwc.shape
+    table, ok = scatter_table(in_h, out_h)
+    if not ok:
+        return None
+    hb, hk, _ = precompute_coeffs(in_w, out_w)
+    src = rgb_hwc.astype(np.uint64)
+    mask32 = np.uint64(0xFFFFFFFF)
+    rnd = np.uint64(1 << (PRECISION_BITS - 1))
+    inter = np.empty((in_h, out_w, 3), dtype=np.uint64)
+    for x in range(out_w):
+        x0, n = int(hb[x, 0]), int(hb[x, 1])
+        k = hk[x, :n].astype(np.uint64)
+        assert (hk[x, :n] >= 0).all()
+        limbs = [(k >> np.uint64(8 * i)) & np.uint64(0xFF) for i in range(3)]
+        s = [np.tensordot(src[:, x0:x0 + n, :], l, axes=([1], [0])) for l in limbs]     # three dot products
+        acc = (rnd + s[0] + (s[1] << np.uint64(8)) + (s[2] << np.uint64(16))) & mask32
+        inter[:, x, :] = acc >> np.uint64(PRECISION_BITS)                                # no clip
+    assert int(inter.max(initial=0)) <= 255
+    out = np.zeros((out_h, out_w, 3), dtype=np.uint8)
+    va = np.full((3, out_w, 3), int(rnd), dtype=np.uint64)       # three output rows in flight
+    vb = np.zeros((3, out_w, 3), dtype=np.uint64)
+    written = np.zeros(out_h, dtype=bool)
+    for r in range(in_h):
+        for j in range(3):
+            va[j] = (va[j] + inter[r] * np.uint64(table[r, j])) & mask32
+        w = int(table[r, 3])
+        if w:
+            oy, j = w >> 2, (w & 3) - 1
+            res = ((va[j] - vb[j]) & mask32) >> np.uint64(PRECISION_BITS)
+            assert int(res.max(initial=0)) <= 255 and not written[oy]
+            out[oy] = res.astype(np.uint8)
+            written[oy] = True
+            vb[j] = (va[j] - rnd) & mask32
+    assert written.all()
+    return out

@@ -36,3 +36,38 @@ def test_preview_layout():
     assert p.shape == (3, 2, 3) and p.dtype == np.float32
     assert p[0, 0, 0] == np.float32((np.float32(0) * np.float32(1 / 255) - np.float32(0.5)) * np.float32(2.0))
     assert p[1, 0, 0] == np.float32(1) * np.float32(1 / 255)
+
+
+# ---- the two reformulations the CUDA band kernel relies on (csrc/resize.cu), checked on the CPU over more
+# ---- geometries than the GPU tests visit: limb dot products without a clip; scatter-form vertical pass
+@pytest.mark.parametrize("in_hw,out_hw", [((1080, 1920), (256, 256)), ((97, 131), (32, 48)), ((300, 257), (64, 96)),
+                                          ((512, 512), (256, 256)), ((257, 256), (256, 256)), ((65, 64), (64, 64)),
+                                          ((1000, 37), (7, 5)), ((531, 257), (256, 129)), ((2160, 384), (256, 32))])
+def test_kernel_arithmetic_model_equals_pillow(in_hw, out_hw):
+    from oracle import kernel_model
+    rng = np.random.default_rng(in_hw[0] * 7 + out_hw[1])
+    img = rng.integers(0, 256, (*in_hw, 3), dtype=np.uint8)
+    img[: in_hw[0] // 3] = 255                                   # saturated rows: the no-clip claim is about these
+    got = kernel_model(img, *out_hw)
+    assert got is not None, "a downscale must be eligible for the scatter form"
+    assert np.array_equal(got, thumbnail_u8(img, *out_hw))
+
+
+def test_scatter_form_eligibility_rule():
+    """Every downscale (scale > 1) qualifies: windows advance monotonically, one output row ends per input row, never
+    more than three over an input row, and every input row's taps are accounted for exactly once.  Upscales with more
+    than one output row per input row do not qualify (the kernel gathers instead)."""
+    from oracle import scatter_table
+    for in_size in list(range(1, 40)) + [97, 255, 256, 257, 511, 1080, 2160, 4096]:
+        for out_size in (1, 2, 3, 5, 16, 31, 64, 100, 256):
+            if out_size >= in_size:
+                continue
+            table, ok = scatter_table(in_size, out_size)
+            assert ok, (in_size, out_size)
+            bounds, kk, _ = precompute_coeffs(in_size, out_size)
+            assert int(table[:, :3].sum()) == int(kk.sum()), (in_size, out_size)
+            ends = table[:, 3][table[:, 3] != 0] >> 2
+            assert np.array_equal(ends, np.arange(out_size)), (in_size, out_size)
+    for in_size in (20, 64, 200, 255):                     # upscales: several output rows end with the same input row
+        assert scatter_table(in_size, 256)[1] is False
+    assert scatter_table(64, 64)[1] is False               # same size: the clipped last window ends with the one before it
