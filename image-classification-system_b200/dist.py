@@ -34,6 +34,28 @@ def shard_range(n: int, rank: int, world_size: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_by_bytes(lengths, world_size: int):
+    """Size-aware sharding of a mixed-size listing (BASELINE config 3; SURVEY.md section 8(e): "size-aware
+    round-robin so bytes/GPU balance").  Greedy longest-first: images are taken by decreasing byte length (ties by
+    listing position) and each goes to the rank that holds the fewest bytes so far (ties to the lowest rank), so the
+    byte totals of any two ranks differ by at most the largest image.  Deterministic — every rank computes the same
+    assignment from the same listing, nothing is exchanged.  Returns one int64 array of listing positions per rank,
+    each in listing order (the global image index that ``global_dedupe`` orders first / last occurrences by)."""
+    import heapq
+
+    import numpy as np
+
+    ln = np.asarray(lengths, dtype=np.int64)
+    order = np.lexsort((np.arange(ln.shape[0]), -ln))
+    heap = [(0, r) for r in range(world_size)]
+    owner = np.empty(ln.shape[0], dtype=np.int32)
+    for i in order:
+        b, r = heapq.heappop(heap)
+        owner[i] = r
+        heapq.heappush(heap, (b + int(ln[i]), r))
+    return [np.nonzero(owner == r)[0].astype(np.int64) for r in range(world_size)]
+
+
 def shard_rows_by_image(image_idx_sorted, n_images: int, rank: int, world_size: int) -> Tuple[int, int, int, int]:
     """Mode M1: shard label rows by image range.  Returns (img_lo, img_hi, row_lo, row_hi) for
     rows sorted by image index (NumPy or torch 1-D)."""

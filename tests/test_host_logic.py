@@ -122,3 +122,29 @@ def test_calcular_delta_classificacao_vs_reference(ref_labels):
         after_active = (set(d["before_active"]) - inativar) | criar | reativar
         after_inactive = (set(d["before_inactive"]) - reativar) | inativar
         assert sorted(after_active) == d["after_active"] and sorted(after_inactive) == d["after_inactive"]
+
+
+def test_shard_by_bytes_balances_a_config3_listing():
+    """config 3 images are squares of side 256 * 2^(pi(g) mod 5); shards must balance BYTES, not
+    counts, cover every image once, keep listing order inside a shard and be the same on every rank."""
+    import numpy as np
+
+    from ics_b200.dist import shard_by_bytes
+
+    rng = np.random.default_rng(0xB200)
+    sides = 256 << (rng.permutation(10_000) % 5)
+    lengths = (sides.astype(np.int64) ** 2) * 3
+    for ws in (1, 2, 3, 4, 8):
+        shards = shard_by_bytes(lengths, ws)
+        again = shard_by_bytes(lengths.tolist(), ws)
+        assert len(shards) == ws and all(np.array_equal(a, b) for a, b in zip(shards, again))
+        allidx = np.concatenate(shards)
+        assert np.array_equal(np.sort(allidx), np.arange(lengths.shape[0]))          # every image exactly once
+        assert all(np.all(np.diff(s) > 0) for s in shards)                           # listing order inside a shard
+        totals = np.array([lengths[s].sum() for s in shards])
+        assert totals.max() - totals.min() <= lengths.max()                          # within one (largest) image
+        if ws > 1:
+            naive = np.array([lengths[r::ws].sum() for r in range(ws)])              # g mod G
+            assert totals.max() <= naive.max()
+    assert [list(s) for s in shard_by_bytes([5, 5, 5], 2)] == [[0, 2], [1]]            # ties: lowest rank, listing order
+    assert [list(s) for s in shard_by_bytes([], 3)] == [[], [], []]
