@@ -28,7 +28,7 @@ for lo in range(0, n_unique, 50):
 torch.cuda.synchronize()
 for i in range(n_unique, n):                                   # images >= n_unique are byte copies (config 5's rule)
     host[i].copy_(host[(i * 2654435761) % n_unique])
-for chunk in (32, 64, 128):
+for chunk in ([int(x) for x in sys.argv[1:]] or (32, 64, 128)):          # chunk sizes to try
     pipe = IngestPipeline(H, W, n, chunk_images=chunk, want_preview=True)
     pipe.run(host)                                             # warm-up
     t0 = time.perf_counter()
