@@ -37,6 +37,18 @@ def _worker(rank, ws, port, out):
         dig = torch.full((3, 32), rank, dtype=torch.uint8)
         gi = torch.arange(3, dtype=torch.int32) + 3 * rank
         all_d, all_i = d.allgather_digests(dig, gi)
+        # size-aware sharding of a mixed-size listing: computed independently on every rank, must be the same split
+        rng = np.random.default_rng(3)
+        lengths = ((256 << (rng.permutation(500) % 5)).astype(np.int64) ** 2) * 3
+        mine = d.shard_by_bytes(lengths, ws)[rank]
+        owned = torch.zeros(500, dtype=torch.int64)
+        owned[torch.from_numpy(mine)] = 1
+        nbytes = torch.tensor([int(lengths[mine].sum())], dtype=torch.int64)
+        both = [torch.zeros(1, dtype=torch.int64) for _ in range(ws)]
+        dist.all_reduce(owned)                       # every image owned by exactly one rank
+        dist.all_gather(both, nbytes)
+        assert bool((owned == 1).all())
+        assert abs(int(both[0]) - int(both[1])) <= int(lengths.max())
         if rank == 0:
             kappa = labels.fleiss_kappa(vec[:k].numpy(), int(vec[k]), int(vec[k + 1]), n_images, n_r)
             out.put((vec.tolist(), all_d[:, 0].tolist(), all_i.tolist(), kappa))
