@@ -20,7 +20,7 @@ from ._lib import B2Error, LIB_PATH  # noqa: F401
 from . import hostapi, ingest, labels, store  # noqa: F401
 from .hostapi import hash_batch, thumbnails  # noqa: F401
 from .ingest import hash_and_dedupe, ingest_batch  # noqa: F401
-from .labels import label_tally, fleiss_kappa, fleiss_kappa_general, TallyResult  # noqa: F401
+from .labels import label_tally, fleiss_kappa, fleiss_kappa_general, fleiss_kappa_from_hist, TallyResult  # noqa: F401
 
 __version__ = "0.1.0"
 

@@ -19,10 +19,12 @@ B2_ERR_CUDA = -2
 B2_ERR_NOT_SORTED = -3
 B2_ERR_NO_DEVICE = -4
 B2_ERR_WORKSPACE = -5
+B2_ERR_NCCL = -6
 
 B2_TALLY_SORTED = 1
-B2_RESIZE_BESIDE_HASH = 1
 B2_PARTIALS_EXTRA = 7
+B2_AGREE_BINS = 1024
+B2_COMM_ID_BYTES = 128
 
 
 class B2Error(RuntimeError):
@@ -62,6 +64,7 @@ SIGNATURES = {
     "b2_last_error": (C.c_char_p, []),
     "b2_init": (C.c_int, [C.c_int]),
     "b2_device_sm_count": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "b2_shutdown": (C.c_int, []),
     "b2_sha256_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp]),
     "b2_digest_hex": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
     "b2_dedupe_workspace_bytes": (C.c_uint64, [C.c_uint32]),
@@ -72,29 +75,39 @@ SIGNATURES = {
     "b2_resize_plan_taps": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), _vp, _vp, C.c_uint64]),
     "b2_resize_normalize_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp,
                                             C.POINTER(C.c_float), C.POINTER(C.c_float), _vp]),
-    "b2_resize_normalize_batch_ex": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp,
-                                               C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32, _vp]),
-    "b2_label_tally_workspace_bytes": (C.c_uint64, [C.c_uint32]),
     "b2_label_tally": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                 _vp, _vp, _vp, C.c_uint64, _vp]),
+                                 _vp, _vp, _vp, _vp]),
     "b2_label_tally_status": (C.c_int, [_vp, C.c_uint32, C.c_uint64]),
     "b2_fleiss_workspace_bytes": (C.c_uint64, [C.c_uint32]),
-    "b2_fleiss_partials": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint64, _vp]),
+    "b2_fleiss_partials": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
     "b2_distinct_images_per_annotator": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp, _vp]),
     "b2_encode_label_rows": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "b2_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),
     "b2_host_free": (C.c_int, [_vp]),
-    "b2_ingest_stream_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int,
-                                          C.POINTER(_vp)]),
-    "b2_ingest_stream_destroy": (C.c_int, [_vp]),
-    "b2_ingest_stream_submit": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "b2_ingest_stream_wait": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "b2_ingest_ring_create": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "b2_ingest_ring_destroy": (C.c_int, [_vp]),
+    "b2_ingest_ring_submit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp, C.c_uint64,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint64)]),
+    "b2_ingest_ring_wait": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "b2_ingest_ring_poll": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
+    "b2_ingest_ring_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_uint64)]),
     "b2_sha256_host": (C.c_int, [C.c_int, _vp, _vp, C.c_uint32, _vp, _vp]),
     "b2_dedupe_host": (C.c_int, [C.c_int, _vp, _vp, C.c_uint32, _vp, C.c_uint64, _vp, _vp, _vp, _vp]),
     "b2_thumbnails_host": (C.c_int, [C.c_int, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp,
                                      C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "b2_label_tally_host": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                      _vp, _vp]),
+                                      _vp, _vp, _vp]),
+    "b2_distinct_images_host": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp]),
+    "b2_comm_unique_id": (C.c_int, [_vp]),
+    "b2_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
+    "b2_comm_destroy": (C.c_int, [_vp]),
+    "b2_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b2_allgather_digests": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp]),
+    "b2_allreduce_i64": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
+    "b2_dedupe_global_workspace_bytes": (C.c_uint64, [C.c_uint32, C.c_uint32]),
+    "b2_dedupe_global": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, C.c_uint64, _vp, _vp, _vp, _vp,
+                                   _vp, C.c_uint64, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb2ingest.so")
-SOURCES = ["api.cu", "sha256.cu", "dedupe.cu", "resize.cu", "tally.cu", "host.cu"]
+SOURCES = ["api.cu", "sha256.cu", "dedupe.cu", "resize.cu", "tally.cu", "host.cu", "ring.cu", "comm.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "b2ingest.h")]
 
 NVCC_FLAGS = [
@@ -67,7 +67,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static", "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static", "-lcuda", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

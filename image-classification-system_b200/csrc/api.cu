@@ -34,7 +34,7 @@ int sm_count() {
 
 }  // namespace b2
 
-extern "C" int b2_version(void) { return 1; }
+extern "C" int b2_version(void) { return 2; }
 
 extern "C" const char *b2_last_error(void) { return b2::error_buffer(); }
 

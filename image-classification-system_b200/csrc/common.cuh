@@ -38,22 +38,6 @@ int fail(int code, const char *fmt, ...);
 int sm_count();   // SMs of the current device (cached per device)
 
 // ---- device-side helpers ---------------------------------------------------------------
-__device__ __forceinline__ uint4 ldg_stream_v4(const void *p) {
-    // 128-bit read-only load that does not allocate in L1: data is touched once.
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint32_t ldg_stream_u32(const void *p) {
-    uint32_t r;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void stg_stream_v4(void *p, uint4 v) {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -122,7 +122,7 @@ dedupe_resolve_kernel(const uint8_t *__restrict__ digests, const uint8_t *__rest
             }
         }
         is_new[i] = fresh;
-        first_index[i] = first;
+        if (first_index) first_index[i] = first;
         if (last_index) last_index[i] = last;
     }
     // block reduction of the two counters
@@ -244,7 +244,7 @@ extern "C" int b2_dedupe(const uint8_t *d_digests, const uint8_t *d_valid, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     B2_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, 3 * sizeof(uint32_t), st));
     if (n == 0) return B2_OK;
-    B2_REQUIRE(d_digests && d_is_new && d_first_index && d_workspace, "b2_dedupe: null pointer");
+    B2_REQUIRE(d_digests && d_is_new && d_workspace, "b2_dedupe: null pointer");
     B2_REQUIRE(n < 0x7fffffffu, "b2_dedupe: n too large");
     B2_REQUIRE((reinterpret_cast<uintptr_t>(d_digests) & 15) == 0, "b2_dedupe: d_digests must be 16-byte aligned");
     B2_REQUIRE(m == 0 || (d_existing && (reinterpret_cast<uintptr_t>(d_existing) & 15) == 0),

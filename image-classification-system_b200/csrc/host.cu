@@ -5,14 +5,7 @@
 // These entry points own the device side themselves — staging buffers, streams, events — so a caller needs
 // nothing but ctypes:
 //
-//   b2_ingest_stream_*   fixed-shape batches of decoded RGB images in host memory
-//                        -> SHA-256 digests, dedupe decision + stats, uint8 thumbnails, float32 previews
-//                        in host memory.  One copy stream feeds the batch to the device in chunks; each chunk's
-//                        hash runs on one of 32 compute streams (SHA-256 is serial per message: one lane
-//                        hashes a 1080p image in ~130 ms however small the chunk, so many small hash kernels
-//                        must overlap each other and the copies), its resize on one of two more, and the
-//                        results are read back while later chunks still arrive.  submit() only enqueues;
-//                        wait() blocks.  Two streams used alternately keep two batches in flight.
+//   b2_sha256_host / b2_dedupe_host / b2_thumbnails_host   the service's 50-file batches (blocking)
 //   b2_label_tally_host  label rows in host memory -> count matrix (optional) + integer Fleiss partials.
 //   b2_host_alloc/free   page-locked host memory (what makes the copies asynchronous and full speed).
 #include "common.cuh"
@@ -29,9 +22,6 @@
 #include <vector>
 
 namespace b2 {
-
-constexpr int kHashStreams = 32;             // a chunk hash runs ~130 ms (1080p) to ~520 ms (4K) whatever its size: enough streams that no chunk queues behind another
-constexpr int kResizeStreams = 2;
 
 // Page-locked staging buffers for the variable-size host calls, recycled between calls (cudaHostAlloc costs
 // milliseconds).  A buffer is owned by one call at a time; the list only grows to what concurrent callers need.
@@ -68,6 +58,11 @@ struct PinnedPool {
         }
         free_list.push_back(Buf{p, bytes});
     }
+    void clear() {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto &b : free_list) cudaFreeHost(b.p);
+        free_list.clear();
+    }
 };
 static PinnedPool g_pinned;
 
@@ -84,34 +79,6 @@ static void keep_pool_memory(int device) {                   // freed device blo
 
 }  // namespace b2
 
-struct b2_ingest_stream {
-    int device = 0;
-    int in_h = 0, in_w = 0, out_h = 0, out_w = 0;
-    uint32_t max_images = 0, chunk = 0;
-    bool want_preview = false;
-    uint64_t L = 0;                       // bytes per image
-    b2_resize_plan *plan = nullptr;
-    uint8_t *d_stage = nullptr;           // max_images * L
-    uint64_t *d_offsets = nullptr, *d_lengths = nullptr;
-    uint8_t *d_digests = nullptr, *d_thumbs = nullptr, *d_is_new = nullptr;
-    float *d_previews = nullptr;
-    int32_t *d_first = nullptr, *d_last = nullptr;
-    uint32_t *d_counts = nullptr;
-    void *d_ws = nullptr;
-    uint64_t ws_bytes = 0;
-    uint8_t *d_existing = nullptr;
-    uint64_t existing_cap = 0;            // digests
-    cudaStream_t copy = nullptr, fin = nullptr;
-    cudaStream_t hash[b2::kHashStreams] = {};
-    cudaStream_t resize[b2::kResizeStreams] = {};
-    std::vector<cudaEvent_t> copied;      // one per chunk
-    cudaEvent_t joined[1 + b2::kHashStreams + b2::kResizeStreams] = {};
-    cudaEvent_t done = nullptr;
-    bool pending = false;
-    uint64_t h2d = 0, d2h = 0;
-    uint32_t launches = 0;
-};
-
 extern "C" int b2_host_alloc(void **p, uint64_t bytes) {
     using namespace b2;
     B2_REQUIRE(p != nullptr && bytes > 0, "b2_host_alloc: bad argument");
@@ -125,193 +92,11 @@ extern "C" int b2_host_free(void *p) {
     return B2_OK;
 }
 
-extern "C" int b2_ingest_stream_destroy(b2_ingest_stream *s) {
-    if (!s) return B2_OK;
-    cudaSetDevice(s->device);
-    if (s->done) cudaEventSynchronize(s->done);
-    if (s->plan) b2_resize_plan_destroy(s->plan);
-    cudaFree(s->d_stage); cudaFree(s->d_offsets); cudaFree(s->d_lengths); cudaFree(s->d_digests);
-    cudaFree(s->d_thumbs); cudaFree(s->d_previews); cudaFree(s->d_is_new); cudaFree(s->d_first);
-    cudaFree(s->d_last); cudaFree(s->d_counts); cudaFree(s->d_ws); cudaFree(s->d_existing);
-    if (s->copy) cudaStreamDestroy(s->copy);
-    if (s->fin) cudaStreamDestroy(s->fin);
-    for (auto st : s->hash) if (st) cudaStreamDestroy(st);
-    for (auto st : s->resize) if (st) cudaStreamDestroy(st);
-    for (auto e : s->copied) cudaEventDestroy(e);
-    for (auto e : s->joined) if (e) cudaEventDestroy(e);
-    if (s->done) cudaEventDestroy(s->done);
-    delete s;
-    return B2_OK;
-}
-
-extern "C" int b2_ingest_stream_create(int device, int in_h, int in_w, int out_h, int out_w, uint32_t max_images,
-                                       uint32_t chunk_images, int want_preview, b2_ingest_stream **out) {
-    using namespace b2;
-    B2_REQUIRE(out != nullptr, "b2_ingest_stream_create: null output");
-    *out = nullptr;
-    B2_REQUIRE(max_images >= 1 && in_h > 0 && in_w > 0, "b2_ingest_stream_create: empty shape or batch");
-    const uint64_t L = uint64_t(in_h) * in_w * 3;
-    B2_REQUIRE(L % 16 == 0, "b2_ingest_stream_create: in_h*in_w*3 must be a multiple of 16 (images are packed back to back)");
-    int rc = b2_init(device);
-    if (rc != B2_OK) return rc;
-    b2_ingest_stream *s = new (std::nothrow) b2_ingest_stream();
-    B2_REQUIRE(s != nullptr, "b2_ingest_stream_create: out of host memory");
-    s->device = device;
-    s->in_h = in_h; s->in_w = in_w; s->out_h = out_h; s->out_w = out_w;
-    s->max_images = max_images;
-    s->chunk = chunk_images < 1 ? 1 : (chunk_images > max_images ? max_images : chunk_images);
-    s->want_preview = want_preview != 0;
-    s->L = L;
-#define B2_TRY(expr)                                                                                    \
-    do {                                                                                                \
-        cudaError_t _e = (expr);                                                                        \
-        if (_e != cudaSuccess) {                                                                        \
-            b2_ingest_stream_destroy(s);                                                                \
-            return fail(B2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-        }                                                                                               \
-    } while (0)
-    rc = b2_resize_plan_create(in_h, in_w, out_h, out_w, &s->plan);
-    if (rc != B2_OK) { b2_ingest_stream_destroy(s); return rc; }
-    const size_t out_px = size_t(out_h) * out_w * 3;
-    B2_TRY(cudaMalloc(&s->d_stage, size_t(max_images) * L));
-    B2_TRY(cudaMalloc(&s->d_offsets, size_t(max_images) * 8));
-    B2_TRY(cudaMalloc(&s->d_lengths, size_t(max_images) * 8));
-    B2_TRY(cudaMalloc(&s->d_digests, size_t(max_images) * 32));
-    B2_TRY(cudaMalloc(&s->d_thumbs, size_t(max_images) * out_px));
-    if (s->want_preview) B2_TRY(cudaMalloc(&s->d_previews, size_t(max_images) * out_px * 4));
-    B2_TRY(cudaMalloc(&s->d_is_new, max_images));
-    B2_TRY(cudaMalloc(&s->d_first, size_t(max_images) * 4));
-    B2_TRY(cudaMalloc(&s->d_last, size_t(max_images) * 4));
-    B2_TRY(cudaMalloc(&s->d_counts, 16));
-    s->ws_bytes = b2_dedupe_workspace_bytes(max_images);
-    B2_TRY(cudaMalloc(&s->d_ws, size_t(s->ws_bytes ? s->ws_bytes : 8)));
-    {
-        std::vector<uint64_t> off(max_images), len(max_images, L);
-        for (uint32_t i = 0; i < max_images; ++i) off[i] = uint64_t(i) * L;
-        B2_TRY(cudaMemcpy(s->d_offsets, off.data(), size_t(max_images) * 8, cudaMemcpyHostToDevice));
-        B2_TRY(cudaMemcpy(s->d_lengths, len.data(), size_t(max_images) * 8, cudaMemcpyHostToDevice));
-    }
-    // The hash kernels are the long pole (~130 ms each whatever the chunk size) and want one warp per SM
-    // sub-partition: their streams get the higher priority, so their CTAs are placed before the resize CTAs.
-    int prio_low = 0, prio_high = 0;
-    B2_TRY(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
-    B2_TRY(cudaStreamCreateWithPriority(&s->copy, cudaStreamNonBlocking, prio_low));
-    B2_TRY(cudaStreamCreateWithPriority(&s->fin, cudaStreamNonBlocking, prio_low));
-    for (auto &st : s->hash) B2_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_high));
-    for (auto &st : s->resize) B2_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_low));
-    const uint32_t n_chunks = (max_images + s->chunk - 1) / s->chunk;
-    s->copied.assign(n_chunks, nullptr);
-    for (auto &e : s->copied) B2_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : s->joined) B2_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    B2_TRY(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
-#undef B2_TRY
-    *out = s;
-    return B2_OK;
-}
-
-extern "C" int b2_ingest_stream_submit(b2_ingest_stream *s, const uint8_t *h_images, uint32_t n,
-                                       const uint8_t *h_existing_sorted, uint64_t m,
-                                       uint8_t *h_digests, uint8_t *h_is_new, int32_t *h_first_index,
-                                       int32_t *h_last_index, uint32_t *h_counts,
-                                       uint8_t *h_thumbs, float *h_previews) {
-    using namespace b2;
-    B2_REQUIRE(s != nullptr, "b2_ingest_stream_submit: null stream");
-    B2_REQUIRE(!s->pending, "b2_ingest_stream_submit: a batch is still in flight (call b2_ingest_stream_wait first)");
-    B2_REQUIRE(n >= 1 && n <= s->max_images && h_images != nullptr, "b2_ingest_stream_submit: 1 <= n <= max_images images required");
-    B2_REQUIRE(h_digests && h_is_new && h_counts && h_thumbs, "b2_ingest_stream_submit: null output pointer");
-    B2_REQUIRE(!h_previews || s->want_preview, "b2_ingest_stream_submit: previews asked from a stream created without them");
-    B2_REQUIRE(m == 0 || h_existing_sorted != nullptr, "b2_ingest_stream_submit: null existing table");
-    B2_CUDA_CHECK(cudaSetDevice(s->device));
-    s->h2d = s->d2h = 0;
-    s->launches = 0;
-    const size_t out_px = size_t(s->out_h) * s->out_w * 3;
-    if (m > s->existing_cap) {                               // grow the table buffer (synchronises; rare)
-        B2_CUDA_CHECK(cudaFree(s->d_existing));
-        s->d_existing = nullptr;
-        s->existing_cap = 0;
-        B2_CUDA_CHECK(cudaMalloc(&s->d_existing, size_t(m) * 32));
-        s->existing_cap = m;
-    }
-    if (m) {
-        B2_CUDA_CHECK(cudaMemcpyAsync(s->d_existing, h_existing_sorted, size_t(m) * 32, cudaMemcpyHostToDevice, s->copy));
-        s->h2d += m * 32;
-    }
-    uint32_t c = 0;
-    for (uint32_t lo = 0; lo < n; lo += s->chunk, ++c) {
-        const uint32_t cnt = n - lo < s->chunk ? n - lo : s->chunk;
-        B2_CUDA_CHECK(cudaMemcpyAsync(s->d_stage + size_t(lo) * s->L, h_images + size_t(lo) * s->L, size_t(cnt) * s->L,
-                                      cudaMemcpyHostToDevice, s->copy));
-        s->h2d += uint64_t(cnt) * s->L;
-        B2_CUDA_CHECK(cudaEventRecord(s->copied[c], s->copy));
-        cudaStream_t hs = s->hash[c % kHashStreams];
-        B2_CUDA_CHECK(cudaStreamWaitEvent(hs, s->copied[c], 0));
-        int rc = b2_sha256_batch(s->d_stage, s->d_offsets + lo, s->d_lengths + lo, nullptr, cnt, s->d_digests + size_t(lo) * 32, hs);
-        if (rc != B2_OK) return rc;
-        cudaStream_t rs = s->resize[c % kResizeStreams];
-        B2_CUDA_CHECK(cudaStreamWaitEvent(rs, s->copied[c], 0));
-        float *d_prev = h_previews ? s->d_previews + size_t(lo) * out_px : nullptr;
-        rc = b2_resize_normalize_batch_ex(s->plan, s->d_stage, s->d_offsets + lo, nullptr, cnt, s->d_thumbs + size_t(lo) * out_px,
-                                          d_prev, nullptr, nullptr, B2_RESIZE_BESIDE_HASH, rs);
-        if (rc != B2_OK) return rc;
-        s->launches += 2;
-        B2_CUDA_CHECK(cudaMemcpyAsync(h_thumbs + size_t(lo) * out_px, s->d_thumbs + size_t(lo) * out_px, size_t(cnt) * out_px,
-                                      cudaMemcpyDeviceToHost, rs));
-        s->d2h += uint64_t(cnt) * out_px;
-        if (h_previews) {
-            B2_CUDA_CHECK(cudaMemcpyAsync(h_previews + size_t(lo) * out_px, d_prev, size_t(cnt) * out_px * 4,
-                                          cudaMemcpyDeviceToHost, rs));
-            s->d2h += uint64_t(cnt) * out_px * 4;
-        }
-    }
-    // join every stream into `fin`, resolve the whole batch there, read the small results back
-    int j = 0;
-    B2_CUDA_CHECK(cudaEventRecord(s->joined[j], s->copy));
-    B2_CUDA_CHECK(cudaStreamWaitEvent(s->fin, s->joined[j++], 0));
-    for (auto st : s->hash) {
-        B2_CUDA_CHECK(cudaEventRecord(s->joined[j], st));
-        B2_CUDA_CHECK(cudaStreamWaitEvent(s->fin, s->joined[j++], 0));
-    }
-    for (auto st : s->resize) {
-        B2_CUDA_CHECK(cudaEventRecord(s->joined[j], st));
-        B2_CUDA_CHECK(cudaStreamWaitEvent(s->fin, s->joined[j++], 0));
-    }
-    int rc = b2_dedupe(s->d_digests, nullptr, nullptr, n, m ? s->d_existing : nullptr, m, s->d_is_new, s->d_first, s->d_last,
-                       s->d_counts, s->d_ws, s->ws_bytes, s->fin);
-    if (rc != B2_OK) return rc;
-    s->launches += 2;
-    B2_CUDA_CHECK(cudaMemcpyAsync(h_digests, s->d_digests, size_t(n) * 32, cudaMemcpyDeviceToHost, s->fin));
-    B2_CUDA_CHECK(cudaMemcpyAsync(h_is_new, s->d_is_new, n, cudaMemcpyDeviceToHost, s->fin));
-    B2_CUDA_CHECK(cudaMemcpyAsync(h_counts, s->d_counts, 12, cudaMemcpyDeviceToHost, s->fin));
-    s->d2h += uint64_t(n) * 33 + 12;
-    if (h_first_index) {
-        B2_CUDA_CHECK(cudaMemcpyAsync(h_first_index, s->d_first, size_t(n) * 4, cudaMemcpyDeviceToHost, s->fin));
-        s->d2h += uint64_t(n) * 4;
-    }
-    if (h_last_index) {
-        B2_CUDA_CHECK(cudaMemcpyAsync(h_last_index, s->d_last, size_t(n) * 4, cudaMemcpyDeviceToHost, s->fin));
-        s->d2h += uint64_t(n) * 4;
-    }
-    B2_CUDA_CHECK(cudaEventRecord(s->done, s->fin));
-    s->pending = true;
-    return B2_OK;
-}
-
-extern "C" int b2_ingest_stream_wait(b2_ingest_stream *s, uint64_t *h2d_bytes, uint64_t *d2h_bytes, uint32_t *kernel_launches) {
-    using namespace b2;
-    B2_REQUIRE(s != nullptr, "b2_ingest_stream_wait: null stream");
-    B2_REQUIRE(s->pending, "b2_ingest_stream_wait: nothing was submitted");
-    B2_CUDA_CHECK(cudaEventSynchronize(s->done));
-    s->pending = false;
-    if (h2d_bytes) *h2d_bytes = s->h2d;
-    if (d2h_bytes) *d2h_bytes = s->d2h;
-    if (kernel_launches) *kernel_launches = s->launches;
-    return B2_OK;
-}
-
 // Label rows in host memory -> (optional) count matrix and partials in host memory.  Blocking.
 extern "C" int b2_label_tally_host(int device, const int32_t *h_image_idx, const uint8_t *h_class_idx,
                                    const uint8_t *h_active, uint64_t rows, uint32_t image_base, uint32_t n_images,
-                                   uint32_t k, uint32_t flags, int32_t *h_counts, int64_t *h_partials) {
+                                   uint32_t k, uint32_t flags, int32_t *h_counts, int64_t *h_partials,
+                                   int64_t *h_agree_hist) {
     using namespace b2;
     B2_REQUIRE(h_partials != nullptr, "b2_label_tally_host: null partials");
     B2_REQUIRE(rows == 0 || (h_image_idx && h_class_idx && h_active), "b2_label_tally_host: null row pointer");
@@ -321,11 +106,12 @@ extern "C" int b2_label_tally_host(int device, const int32_t *h_image_idx, const
     cudaStream_t st = nullptr;
     int32_t *d_img = nullptr, *d_counts = nullptr;
     uint8_t *d_cls = nullptr, *d_act = nullptr;
-    int64_t *d_part = nullptr;
+    int64_t *d_part = nullptr, *d_hist = nullptr;
     // stream-ordered allocations: served from the device's memory pool after the first call, no device-wide
     // synchronisation on free
     auto cleanup = [&]() {
         if (st) {
+            if (d_hist) cudaFreeAsync(d_hist, st);
             if (d_img) cudaFreeAsync(d_img, st);
             if (d_cls) cudaFreeAsync(d_cls, st);
             if (d_act) cudaFreeAsync(d_act, st);
@@ -351,19 +137,69 @@ extern "C" int b2_label_tally_host(int device, const int32_t *h_image_idx, const
     B2_TRY(cudaMallocAsync(&d_act, r, st));
     B2_TRY(cudaMallocAsync(&d_counts, size_t(n_images) * k * 4, st));
     B2_TRY(cudaMallocAsync(&d_part, (size_t(k) + B2_PARTIALS_EXTRA) * 8, st));
+    if (h_agree_hist) B2_TRY(cudaMallocAsync(&d_hist, size_t(B2_AGREE_BINS) * 8, st));
     if (rows) {
         B2_TRY(cudaMemcpyAsync(d_img, h_image_idx, rows * 4, cudaMemcpyHostToDevice, st));
         B2_TRY(cudaMemcpyAsync(d_cls, h_class_idx, rows, cudaMemcpyHostToDevice, st));
         B2_TRY(cudaMemcpyAsync(d_act, h_active, rows, cudaMemcpyHostToDevice, st));
     }
-    rc = b2_label_tally(d_img, d_cls, d_act, rows, image_base, n_images, k, flags, d_counts, d_part, nullptr, 0, st);
+    rc = b2_label_tally(d_img, d_cls, d_act, rows, image_base, n_images, k, flags, d_counts, d_part, d_hist, st);
     if (rc != B2_OK) { cleanup(); return rc; }
     B2_TRY(cudaMemcpyAsync(h_partials, d_part, (size_t(k) + B2_PARTIALS_EXTRA) * 8, cudaMemcpyDeviceToHost, st));
+    if (h_agree_hist) B2_TRY(cudaMemcpyAsync(h_agree_hist, d_hist, size_t(B2_AGREE_BINS) * 8, cudaMemcpyDeviceToHost, st));
     if (h_counts) B2_TRY(cudaMemcpyAsync(h_counts, d_counts, size_t(n_images) * k * 4, cudaMemcpyDeviceToHost, st));
     B2_TRY(cudaStreamSynchronize(st));
 #undef B2_TRY
     cleanup();
     return b2_label_tally_status(h_partials, k, rows);
+}
+
+// Rows sorted by (annotator, image) in host memory -> distinct active images per annotator in host memory
+// (the bulk form of app/api/routes/classificacoes.py:224-230).  Blocking.
+extern "C" int b2_distinct_images_host(int device, const int32_t *h_annotator_idx, const int32_t *h_image_idx,
+                                       const uint8_t *h_active, uint64_t rows, uint32_t n_annotators,
+                                       uint32_t *h_distinct) {
+    using namespace b2;
+    B2_REQUIRE(h_distinct != nullptr && n_annotators >= 1, "b2_distinct_images_host: bad output");
+    B2_REQUIRE(rows == 0 || (h_annotator_idx && h_image_idx && h_active), "b2_distinct_images_host: null row pointer");
+    int rc = b2_init(device);
+    if (rc != B2_OK) return rc;
+    keep_pool_memory(device);
+    cudaStream_t st = nullptr;
+    uint8_t *d = nullptr;
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t r = size_t(rows ? rows : 1);
+    const size_t o_ann = 0, o_img = up(r * 4), o_act = o_img + up(r * 4), o_out = o_act + up(r), bytes = o_out + up(size_t(n_annotators) * 4);
+    auto cleanup = [&]() {
+        if (st) {
+            if (d) cudaFreeAsync(d, st);
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    };
+#define B2_TRY(expr)                                                                                    \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            cleanup();                                                                                  \
+            return fail(B2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                               \
+    } while (0)
+    B2_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    B2_TRY(cudaMallocAsync(&d, bytes, st));
+    if (rows) {
+        B2_TRY(cudaMemcpyAsync(d + o_ann, h_annotator_idx, rows * 4, cudaMemcpyHostToDevice, st));
+        B2_TRY(cudaMemcpyAsync(d + o_img, h_image_idx, rows * 4, cudaMemcpyHostToDevice, st));
+        B2_TRY(cudaMemcpyAsync(d + o_act, h_active, rows, cudaMemcpyHostToDevice, st));
+    }
+    rc = b2_distinct_images_per_annotator(reinterpret_cast<const int32_t *>(d + o_ann), reinterpret_cast<const int32_t *>(d + o_img),
+                                          d + o_act, rows, n_annotators, reinterpret_cast<uint32_t *>(d + o_out), st);
+    if (rc != B2_OK) { cleanup(); return rc; }
+    B2_TRY(cudaMemcpyAsync(h_distinct, d + o_out, size_t(n_annotators) * 4, cudaMemcpyDeviceToHost, st));
+    B2_TRY(cudaStreamSynchronize(st));
+#undef B2_TRY
+    cleanup();
+    return B2_OK;
 }
 
 // ---- variable-size messages in host memory (the service's 50-file batches) -------------------------------
@@ -533,13 +369,42 @@ struct PlanCache {
         b2_resize_plan *pl = nullptr;
         const int rc = b2_resize_plan_create(ih, iw, oh, ow, &pl);
         if (rc != B2_OK) return rc;
-        plans[key] = pl;                                     // plans live as long as the library
+        plans[key] = pl;                                     // plans live until b2_shutdown()
         *out = pl;
         return B2_OK;
     }
+    void clear() {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto &kv : plans) {
+            cudaSetDevice(std::get<0>(kv.first));
+            b2_resize_plan_destroy(kv.second);
+        }
+        plans.clear();
+    }
 };
 static PlanCache g_plans;
+
+// Tap plan for one (device, shape) pair, created on first use and shared by the host-pointer entry points
+// (b2_thumbnails_host, b2_ingest_ring_*).  The current device must be `device`.
+int cached_plan(int device, int ih, int iw, int oh, int ow, b2_resize_plan **out) {
+    return g_plans.get(device, ih, iw, oh, ow, out);
+}
 }  // namespace b2
+
+// Release what the host-pointer entry points keep between calls: the pool of page-locked staging buffers and the
+// cached resize plans (b2_shutdown).  Objects the caller created (plans, rings,
+// communicators) are the caller's to destroy first; no other call may be in flight.  The library can be used
+// again afterwards (everything is re-created on demand).
+extern "C" int b2_shutdown(void) {
+    using namespace b2;
+    int dev = 0;
+    const bool have_dev = cudaGetDevice(&dev) == cudaSuccess;
+    g_plans.clear();
+    g_pinned.clear();
+    if (have_dev) cudaSetDevice(dev);
+    cudaGetLastError();
+    return B2_OK;
+}
 
 extern "C" int b2_thumbnails_host(int device, const uint8_t *const *h_rgb, const uint32_t *h_hw, uint32_t n,
                                   uint32_t out_h, uint32_t out_w, uint8_t *h_thumbs, float *h_previews,

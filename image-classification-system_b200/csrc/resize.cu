@@ -618,13 +618,6 @@ extern "C" int b2_resize_normalize_batch(const b2_resize_plan *pl, const uint8_t
                                          const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,
                                          uint8_t *d_thumb, float *d_preview, const float mean[3],
                                          const float inv_std[3], void *stream) {
-    return b2_resize_normalize_batch_ex(pl, d_rgb, d_offsets, d_out_slot, n, d_thumb, d_preview, mean, inv_std, 0u, stream);
-}
-
-extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint8_t *d_rgb,
-                                            const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,
-                                            uint8_t *d_thumb, float *d_preview, const float mean[3],
-                                            const float inv_std[3], uint32_t flags, void *stream) {
     using namespace b2;
     if (n == 0) return B2_OK;
     B2_REQUIRE(pl && d_rgb && d_offsets && d_thumb, "b2_resize_normalize_batch: null pointer");
@@ -661,7 +654,6 @@ extern "C" int b2_resize_normalize_batch_ex(const b2_resize_plan *pl, const uint
         p.mean[c] = mean ? mean[c] : 0.0f;
         p.inv_std[c] = inv_std ? inv_std[c] : 1.0f;
     }
-    (void)flags;   // B2_RESIZE_BESIDE_HASH is accepted and ignored: one horizontal pass serves both situations now
     const bool fast = pl->q_bucket != 0 && resize_path_override() != 1 &&
                       uint64_t(n) * uint64_t(p.n_bands) < 0x7fffffffull;
     if (!fast) {

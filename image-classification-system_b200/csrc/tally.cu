@@ -24,8 +24,10 @@ namespace b2 {
 
 constexpr int kTallyThreads = 512;
 constexpr int kRowsPerThread = 16;
-constexpr int kTileBudgetBytes = 100 * 1024;                    // two CTAs per SM
+constexpr int kTileBudgetBytes = 92 * 1024;                     // two CTAs per SM (beside the 8 KB agreement histogram)
 constexpr int kMaxTileImages = 512;
+
+constexpr uint32_t kAgreeBins = B2_AGREE_BINS;
 
 // indices into d_partials after the k class totals
 enum { P_S2 = 0, P_R = 1, P_RATED = 2, P_PAIR_IMAGES = 3, P_PAIRS = 4, P_ROWS_SEEN = 5, P_UNSORTED = 6 };
@@ -43,6 +45,19 @@ __device__ __forceinline__ void part_add(unsigned long long *s_part, int which, 
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_part[which], v);
 }
 
+// Agreement histogram (general-n Fleiss kappa without a second pass, exact for any sharding): bin n (2 <= n <
+// kAgreeBins) accumulates sum_j n_ij^2 - n_i over the images with n_i = n, so that sum_i P_i =
+// sum_n bin[n] / (n (n - 1)) is computed on the host from INTEGERS; bin 0 counts the images with n_i >= kAgreeBins
+// (the caller then falls back to b2_fleiss_partials' float64 sum), bin 1 stays 0.
+__device__ __forceinline__ void agree_add(unsigned long long *s_hist, uint32_t n, uint32_t s2) {
+    if (n >= kAgreeBins) atomicAdd(&s_hist[0], 1ull);
+    else if (n >= 2u) atomicAdd(&s_hist[n], (unsigned long long)(s2 - n));
+}
+__device__ __forceinline__ void commit_hist(const unsigned long long *s_hist, unsigned long long *g_hist) {
+    for (uint32_t i = threadIdx.x; i < kAgreeBins; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&g_hist[i], s_hist[i]);
+}
+
 // Add the CTA's partials to global memory (integer atomics: exact, order-independent).
 __device__ void commit_partials(const unsigned long long *s_part, const unsigned long long *s_class_tot, uint32_t k,
                                 unsigned long long *g_partials) {
@@ -56,7 +71,8 @@ __device__ void commit_partials(const unsigned long long *s_part, const unsigned
 // n_i and the quantities derived from it.  Leaves the tile zeroed.  Caller syncs before and after.
 template <bool kStore, bool kSumPi>
 __device__ __noinline__ void flush_tile(int32_t *tile, uint32_t n_img, uint32_t k, int32_t *g_counts,
-                                        unsigned long long *s_class_tot, unsigned long long *s_part, double *sum_pi) {
+                                        unsigned long long *s_class_tot, unsigned long long *s_part, double *sum_pi,
+                                        unsigned long long *s_hist) {
     const uint32_t elems = n_img * k;
     uint32_t c = threadIdx.x % k;
     const uint32_t cstep = blockDim.x % k;
@@ -84,7 +100,10 @@ __device__ __noinline__ void flush_tile(int32_t *tile, uint32_t n_img, uint32_t 
         rated += n >= 1;
         pair_images += n >= 2;
         pairs += n * (n - (n > 0));
-        if (kSumPi && n >= 2) *sum_pi += double(s2 - n) / double(n * (n - 1));
+        if (kSumPi && n >= 2) {
+            if (sum_pi) *sum_pi += double(s2 - n) / double(n * (n - 1));
+            if (s_hist) agree_add(s_hist, n > 0xffffffffull ? 0xffffffffu : uint32_t(n), uint32_t(s2));
+        }
     }
     part_add(s_part, P_S2, s2_all);
     part_add(s_part, P_R, r);
@@ -133,6 +152,7 @@ struct TallySmem {
     unsigned long long *class_tot;        // k
     unsigned long long *part;             // 8 (7 used)
     double *dred;                         // blockDim (fleiss_partials_kernel only)
+    unsigned long long *hist;             // kAgreeBins
 };
 __device__ __forceinline__ TallySmem carve_smem(uint8_t *raw, uint32_t tile_images, uint32_t k) {
     TallySmem s;
@@ -141,6 +161,7 @@ __device__ __forceinline__ TallySmem carve_smem(uint8_t *raw, uint32_t tile_imag
     s.class_tot = reinterpret_cast<unsigned long long *>(raw + tile_bytes);
     s.part = s.class_tot + k;
     s.dred = reinterpret_cast<double *>(s.part + 8);
+    s.hist = reinterpret_cast<unsigned long long *>(s.dred + kTallyThreads);
     return s;
 }
 
@@ -174,7 +195,7 @@ constexpr int kSlabWarps = kSlabThreads / 32;
 
 __host__ __device__ inline size_t slab_smem_bytes(uint32_t stages, uint32_t tile_images, uint32_t k) {
     return size_t(stages) * kSlabStageBytes + ((size_t(tile_images) * k * 4 + 15) & ~size_t(15)) + 1024 +
-           size_t(k) * 8 + 8 * 8 + 16 + size_t(stages) * 8;
+           size_t(k) * 8 + 8 * 8 + 16 + size_t(stages) * 8 + size_t(kAgreeBins) * 8;
 }
 
 // One row of a quad, branch-free: in the window and class in range => seen++; also active => one shared
@@ -239,7 +260,7 @@ __global__ void __launch_bounds__(kSlabThreads, 2)
 tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
                   const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
                   uint32_t k, uint32_t tile_log2, int32_t *__restrict__ counts,
-                  unsigned long long *__restrict__ g_partials) {
+                  unsigned long long *__restrict__ g_partials, unsigned long long *__restrict__ g_hist) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t T = 1u << tile_log2, tmask = T - 1u;
     uint8_t *ring = smem_raw;
@@ -249,6 +270,7 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
     unsigned long long *part = class_tot + k;                    // 8 (7 used)
     int32_t *s_beyond = reinterpret_cast<int32_t *>(part + 8);   // 1 (+ padding to 16 bytes)
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_beyond + 4);
+    unsigned long long *hist = reinterpret_cast<unsigned long long *>(bars + NS);   // kAgreeBins (used when g_hist != NULL)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
 
     const uint32_t G = gridDim.x, b = blockIdx.x;
@@ -274,6 +296,8 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
 
     for (uint32_t e = tid; e < T * k; e += kSlabThreads) tile[e] = 0;
     for (uint32_t c = tid; c < k + 8; c += kSlabThreads) class_tot[c] = 0;      // class totals + partials
+    if (g_hist)
+        for (uint32_t c = tid; c < kAgreeBins; c += kSlabThreads) hist[c] = 0;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
@@ -286,10 +310,11 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
     uint32_t rated = 0, pair_images = 0;
 #pragma unroll
     for (int cc = 0; cc < KC; ++cc) tot[cc] = 0;
-    auto fold_image = [&](uint32_t n) {                           // n_i of one image (0 is harmless)
+    auto fold_image = [&](uint32_t n, uint32_t s2i) {             // n_i and sum_j n_ij^2 of one image (0 is harmless)
         rated += n >= 1u;
         pair_images += n >= 2u;
         pairs += (unsigned long long)n * (n - 1u);                // 0 * 0xffffffff = 0
+        if (g_hist) agree_add(hist, n, s2i);                      // s2i may have wrapped for n >= 65536: unused from kAgreeBins up
     };
 
     // Write images [a, e) (complete, all mine) to d_counts, fold them into the partials, leave their
@@ -300,12 +325,12 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
         __syncthreads();
         const uint32_t total = uint32_t(e - a);
         const uint32_t n_ring = total < T ? total : T;
-        uint32_t n_mine = 0, it = 0;
+        uint32_t n_mine = 0, s2_mine = 0, it = 0;
         for (uint32_t i = wid; i < n_ring; i += kSlabWarps, ++it) {
             const int32_t img = a + int32_t(i);
             int32_t *src = tile + (uint32_t(img) & tmask) * k;
             int32_t *dst = counts + size_t(img - image_base) * k;
-            uint32_t v[KC], n = 0;
+            uint32_t v[KC], n = 0, s2i = 0;
 #pragma unroll
             for (int cc = 0; cc < KC; ++cc) {
                 const uint32_t c = lane + 32u * cc;
@@ -320,13 +345,15 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
                 }
                 tot[cc] += v[cc];
                 s2 += (unsigned long long)v[cc] * v[cc];
+                s2i += v[cc] * v[cc];
                 n += v[cc];
             }
             n = __reduce_add_sync(0xffffffffu, n);
-            if ((it & 31u) == lane) n_mine = n;
-            if ((it & 31u) == 31u) { fold_image(n_mine); n_mine = 0; }
+            if (g_hist) s2i = __reduce_add_sync(0xffffffffu, s2i);
+            if ((it & 31u) == lane) { n_mine = n; s2_mine = s2i; }
+            if ((it & 31u) == 31u) { fold_image(n_mine, s2_mine); n_mine = 0; s2_mine = 0; }
         }
-        fold_image(n_mine);
+        fold_image(n_mine, s2_mine);
         if (total > n_ring) {                                     // images without rows
             int32_t *z = counts + size_t(a - image_base + int32_t(n_ring)) * k;
             const size_t ne = size_t(total - n_ring) * k;
@@ -509,6 +536,7 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
     part_add(part, P_UNSORTED, unsorted);
     __syncthreads();
     commit_partials(part, class_tot, k, g_partials);
+    if (g_hist) commit_hist(hist, g_hist);
 }
 
 // Any row order: one RED.ADD per active row into a zeroed count matrix.
@@ -546,13 +574,16 @@ tally_scatter_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__res
 __global__ void __launch_bounds__(kTallyThreads, 2)
 fleiss_partials_kernel(const int32_t *__restrict__ counts, uint32_t n_images, uint32_t k, uint32_t tile_images,
                        unsigned long long *__restrict__ g_partials, double *__restrict__ sum_pi_out,
-                       double *__restrict__ block_sums, unsigned int *__restrict__ ticket) {
+                       double *__restrict__ block_sums, unsigned int *__restrict__ ticket,
+                       unsigned long long *__restrict__ g_hist) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const TallySmem sm = carve_smem(smem_raw, tile_images, k);
     int32_t *tile = sm.tile;
     double *s_dred = sm.dred;
 
     for (uint32_t c = threadIdx.x; c < k + 8; c += blockDim.x) sm.class_tot[c] = 0;
+    if (g_hist)
+        for (uint32_t c = threadIdx.x; c < kAgreeBins; c += blockDim.x) sm.hist[c] = 0;
     double my_pi = 0.0;
     const uint32_t n_tiles = (n_images + tile_images - 1) / tile_images;
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -562,11 +593,14 @@ fleiss_partials_kernel(const int32_t *__restrict__ counts, uint32_t n_images, ui
         __syncthreads();
         for (uint32_t e = threadIdx.x; e < n_img * k; e += blockDim.x) tile[e] = __ldg(src + e);
         __syncthreads();
-        if (sum_pi_out) flush_tile<false, true>(tile, n_img, k, nullptr, sm.class_tot, sm.part, &my_pi);
-        else flush_tile<false, false>(tile, n_img, k, nullptr, sm.class_tot, sm.part, nullptr);
+        if (sum_pi_out || g_hist)
+            flush_tile<false, true>(tile, n_img, k, nullptr, sm.class_tot, sm.part, sum_pi_out ? &my_pi : nullptr,
+                                    g_hist ? sm.hist : nullptr);
+        else flush_tile<false, false>(tile, n_img, k, nullptr, sm.class_tot, sm.part, nullptr, nullptr);
     }
     __syncthreads();
     commit_partials(sm.part, sm.class_tot, k, g_partials);
+    if (g_hist) commit_hist(sm.hist, g_hist);
     if (sum_pi_out) {
         s_dred[threadIdx.x] = my_pi;
         __syncthreads();
@@ -598,7 +632,7 @@ static uint32_t pick_tile_images(uint32_t k) {
 }
 static size_t tally_smem_bytes(uint32_t tile_images, uint32_t k) {
     size_t tile = (size_t(tile_images) * k * 4 + 7) & ~size_t(7);
-    return tile + size_t(k) * 8 + 8 * 8 + size_t(kTallyThreads) * 8;
+    return tile + size_t(k) * 8 + 8 * 8 + size_t(kTallyThreads) * 8 + size_t(kAgreeBins) * 8;
 }
 constexpr uint32_t kFleissGridMax = 592;
 
@@ -608,11 +642,6 @@ static cudaError_t ensure_smem(const void *fn, size_t bytes) {
 
 }  // namespace b2
 
-extern "C" uint64_t b2_label_tally_workspace_bytes(uint32_t n_images) {
-    (void)n_images;
-    return 0;
-}
-
 extern "C" uint64_t b2_fleiss_workspace_bytes(uint32_t n_images) {
     (void)n_images;
     return 16 + 8ull * b2::kFleissGridMax;
@@ -620,11 +649,10 @@ extern "C" uint64_t b2_fleiss_workspace_bytes(uint32_t n_images) {
 
 extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
                               uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
-                              int32_t *d_counts, int64_t *d_partials, void *d_workspace,
-                              uint64_t workspace_bytes, void *stream) {
+                              int32_t *d_counts, int64_t *d_partials, int64_t *d_agree_hist, void *stream) {
     using namespace b2;
-    (void)d_workspace; (void)workspace_bytes;
     B2_REQUIRE(d_counts && d_partials, "b2_label_tally: null output pointer");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(d_agree_hist) & 7) == 0, "b2_label_tally: misaligned histogram");
     B2_REQUIRE(k >= 1 && k <= 256, "b2_label_tally: k must be in 1..256 (class_idx is uint8)");
     B2_REQUIRE(n_images >= 1 && uint64_t(n_images) * k < (1ull << 40), "b2_label_tally: n_images out of range");
     B2_REQUIRE(uint64_t(image_base) + n_images <= 0x7fffffffull, "b2_label_tally: image range exceeds int32");
@@ -635,7 +663,9 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
                "b2_label_tally: misaligned output");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned long long *partials = reinterpret_cast<unsigned long long *>(d_partials);
+    unsigned long long *hist = reinterpret_cast<unsigned long long *>(d_agree_hist);
     B2_CUDA_CHECK(cudaMemsetAsync(partials, 0, (size_t(k) + B2_PARTIALS_EXTRA) * 8, st));
+    if (hist) B2_CUDA_CHECK(cudaMemsetAsync(hist, 0, size_t(kAgreeBins) * 8, st));
     const uint32_t tile_images = pick_tile_images(k);
     const size_t smem = tally_smem_bytes(tile_images, k);
     if (flags & B2_TALLY_SORTED) {                           // thread-per-row slab kernel
@@ -655,7 +685,7 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
         auto launch = [&](auto kern) -> int {
             B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(kern), smem_slab));
             kern<<<uint32_t(want), kSlabThreads, smem_slab, st>>>(d_image_idx, d_class_idx, d_active, rows,
-                                                                 int32_t(image_base), n_images, k, t, d_counts, partials);
+                                                                 int32_t(image_base), n_images, k, t, d_counts, partials, hist);
             B2_LAUNCH_CHECK("tally_slab_kernel");
             return B2_OK;
         };
@@ -693,19 +723,23 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
     const uint32_t n_tiles = (n_images + tile_images - 1) / tile_images;
     const uint32_t grid = n_tiles < kFleissGridMax ? n_tiles : kFleissGridMax;
     fleiss_partials_kernel<<<grid, kTallyThreads, smem, st>>>(d_counts, n_images, k, tile_images, partials,
-                                                             nullptr, nullptr, nullptr);
+                                                             nullptr, nullptr, nullptr, hist);
     B2_LAUNCH_CHECK("fleiss_partials_kernel");
     return B2_OK;
 }
 
 extern "C" int b2_fleiss_partials(const int32_t *d_counts, uint32_t n_images, uint32_t k, int64_t *d_partials,
-                                  double *d_sum_pi, void *d_workspace, uint64_t workspace_bytes, void *stream) {
+                                  double *d_sum_pi, int64_t *d_agree_hist, void *d_workspace, uint64_t workspace_bytes,
+                                  void *stream) {
     using namespace b2;
     B2_REQUIRE(d_counts && d_partials, "b2_fleiss_partials: null pointer");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(d_agree_hist) & 7) == 0, "b2_fleiss_partials: misaligned histogram");
     B2_REQUIRE(k >= 1 && k <= 256 && n_images >= 1, "b2_fleiss_partials: bad shape");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned long long *partials = reinterpret_cast<unsigned long long *>(d_partials);
+    unsigned long long *hist = reinterpret_cast<unsigned long long *>(d_agree_hist);
     B2_CUDA_CHECK(cudaMemsetAsync(partials, 0, (size_t(k) + B2_PARTIALS_EXTRA) * 8, st));
+    if (hist) B2_CUDA_CHECK(cudaMemsetAsync(hist, 0, size_t(kAgreeBins) * 8, st));
     const uint32_t tile_images = pick_tile_images(k);
     const size_t smem = tally_smem_bytes(tile_images, k);
     B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(fleiss_partials_kernel), smem));
@@ -724,7 +758,7 @@ extern "C" int b2_fleiss_partials(const int32_t *d_counts, uint32_t n_images, ui
         B2_CUDA_CHECK(cudaMemsetAsync(ticket, 0, 16, st));
     }
     fleiss_partials_kernel<<<grid, kTallyThreads, smem, st>>>(d_counts, n_images, k, tile_images, partials,
-                                                             d_sum_pi, block_sums, ticket);
+                                                             d_sum_pi, block_sums, ticket, hist);
     B2_LAUNCH_CHECK("fleiss_partials_kernel");
     return B2_OK;
 }
@@ -743,39 +777,42 @@ extern "C" int b2_label_tally_status(const int64_t *h_partials, uint32_t k, uint
 }
 
 // Bulk COUNT(DISTINCT id_img) WHERE id_con = ? AND ativo (app/api/routes/classificacoes.py:224-230)
-// for every annotator at once.  Rows sorted by (annotator_idx, image_idx): an active row opens a
-// new distinct image iff no earlier active row of the same annotator has the same image.
+// for every annotator at once.  Rows sorted by (annotator_idx, image_idx): a run of equal (annotator, image)
+// counts once iff it holds an active row.
 namespace b2 {
 __global__ void __launch_bounds__(256)
 distinct_images_kernel(const int32_t *__restrict__ annotator_idx, const int32_t *__restrict__ image_idx,
                        const uint8_t *__restrict__ active, uint64_t rows, uint32_t n_annotators,
                        uint32_t *__restrict__ distinct) {
-    // A warp takes 32 consecutive rows per step.  Rows are sorted by (annotator, image), so a warp sees one or two
-    // annotators: lanes with the same annotator are grouped with MATCH.ANY and the group's first lane adds the
-    // number of "first active row of its (annotator, image) run" flags in one atomic — 32x fewer atomics than one
-    // per row, and no two lanes of a warp instruction on the same address.
+    // A warp takes 32 consecutive rows per step.  The row that STARTS a run (its key differs from the row before:
+    // one shuffle, lane 0 loads its predecessor) scans the run forward until it meets an active row, so every row
+    // is visited by at most one scanning thread — linear in the table whatever the run lengths (a backward scan
+    // from every row was quadratic on long runs of inactive rows).  A warp sees one or two annotators: lanes with
+    // the same annotator are grouped with MATCH.ANY and the group's first lane adds the group's count in one
+    // atomic — no two lanes of a warp instruction on the same address.
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
     const uint64_t n_warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
     for (uint64_t base = warp * 32; base < rows; base += n_warps * 32) {
         const uint64_t r = base + lane;
-        bool first = false;
-        int32_t a = -1;
-        if (r < rows) {
-            a = annotator_idx[r];
-            if (active[r] && a >= 0 && uint32_t(a) < n_annotators) {
-                const int32_t img = image_idx[r];
-                first = true;                                  // unless an earlier active row of the same run exists
-                for (uint64_t q = r; q-- > 0;) {
-                    if (annotator_idx[q] != a || image_idx[q] != img) break;
-                    if (active[q]) { first = false; break; }
-                }
+        int32_t a = -1, img = -1;
+        if (r < rows) { a = annotator_idx[r]; img = image_idx[r]; }
+        int32_t pa = __shfl_up_sync(0xffffffffu, a, 1), pi = __shfl_up_sync(0xffffffffu, img, 1);
+        if (lane == 0) {
+            pa = base > 0 ? annotator_idx[base - 1] : -1;
+            pi = base > 0 ? image_idx[base - 1] : -1;
+        }
+        bool counted = false;
+        if (r < rows && a >= 0 && uint32_t(a) < n_annotators && (r == 0 || pa != a || pi != img)) {
+            for (uint64_t q = r; q < rows; ++q) {
+                if (q != r && (annotator_idx[q] != a || image_idx[q] != img)) break;
+                if (active[q]) { counted = true; break; }
             }
         }
-        const uint32_t flags = __ballot_sync(0xffffffffu, first);
+        const uint32_t flags = __ballot_sync(0xffffffffu, counted);
         const uint32_t same = __match_any_sync(0xffffffffu, a);
         const uint32_t mine = flags & same;
-        if (first && (mine & ((1u << lane) - 1u)) == 0) atomicAdd(&distinct[a], uint32_t(__popc(mine)));
+        if (counted && (mine & ((1u << lane) - 1u)) == 0) atomicAdd(&distinct[a], uint32_t(__popc(mine)));
     }
 }
 }  // namespace b2

@@ -31,11 +31,17 @@ def init(device: Optional[int] = None) -> int:
         check(lib.b2_init(0 if device is None else int(device)))
         raise B2Error(_lib.B2_ERR_NO_DEVICE, "no CUDA device")
     dev = torch.cuda.current_device() if device is None else int(device)
-    if getattr(_tls, "device", None) != dev:
+    # the cache only skips the capability check: the CURRENT device is compared on every call, because the caller
+    # may have switched it in between (`with torch.cuda.device(1): ...`) and the library launches on the current one
+    if torch.cuda.current_device() != dev:
         torch.cuda.set_device(dev)
-        torch.cuda.current_stream()          # make sure torch created the primary context
+    checked = getattr(_tls, "checked", None)
+    if checked is None:
+        checked = _tls.checked = set()
+    if dev not in checked:
+        torch.cuda.current_stream(dev)       # make sure torch created the primary context
         check(lib.b2_init(dev))
-        _tls.device = dev
+        checked.add(dev)
     return dev
 
 
@@ -75,7 +81,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(torch.cuda.current_device()).cuda_stream
 
 
 def _need_cuda(*tensors: Optional[torch.Tensor]) -> None:
@@ -236,12 +242,9 @@ class ResizePlan:
     def run(self, rgb: torch.Tensor, offsets: torch.Tensor, thumb: Optional[torch.Tensor] = None,
             preview: Optional[torch.Tensor] = None, want_preview: bool = True,
             mean: Sequence[float] = (0.0, 0.0, 0.0), inv_std: Sequence[float] = (1.0, 1.0, 1.0),
-            out_slot: Optional[torch.Tensor] = None, beside_hash: bool = False):
+            out_slot: Optional[torch.Tensor] = None):
         """rgb: uint8 device buffer holding n HWC images at byte ``offsets`` (int64[n]).
-        Returns (thumb uint8[n,out_h,out_w,3], preview float32[n,3,out_h,out_w] or None).
-        ``beside_hash``: a hash kernel runs on another stream at the same time (B2_RESIZE_BESIDE_HASH; kept for
-        callers of the first interface — the kernel now has one horizontal pass that is the faster one in both
-        situations, so the flag changes nothing)."""
+        Returns (thumb uint8[n,out_h,out_w,3], preview float32[n,3,out_h,out_w] or None)."""
         _need_cuda(rgb, offsets, thumb, preview, out_slot)
         init(rgb.device.index)
         n = offsets.numel()
@@ -254,9 +257,8 @@ class ResizePlan:
             preview = torch.empty((n, 3, self.out_h, self.out_w), dtype=torch.float32, device=rgb.device)
         m = (C.c_float * 3)(*[float(x) for x in mean])
         s = (C.c_float * 3)(*[float(x) for x in inv_std])
-        check(lib.b2_resize_normalize_batch_ex(self._h, _ptr(rgb), _ptr(offsets), _ptr(out_slot), n,
-                                               _ptr(thumb), _ptr(preview), m, s,
-                                               _lib.B2_RESIZE_BESIDE_HASH if beside_hash else 0, _stream()))
+        check(lib.b2_resize_normalize_batch(self._h, _ptr(rgb), _ptr(offsets), _ptr(out_slot), n,
+                                            _ptr(thumb), _ptr(preview), m, s, _stream()))
         return thumb, preview
 
 
@@ -302,11 +304,15 @@ def thumbnails(images: Sequence[np.ndarray], out_h: int = 256, out_w: int = 256,
 # --------------------------------------------------------------------------- a13: tally
 def label_tally_device(image_idx: torch.Tensor, class_idx: torch.Tensor, active: torch.Tensor,
                        n_images: int, k: int, image_base: int = 0, sorted_by_image: bool = True,
-                       counts: Optional[torch.Tensor] = None, partials: Optional[torch.Tensor] = None):
+                       counts: Optional[torch.Tensor] = None, partials: Optional[torch.Tensor] = None,
+                       agree_hist: Optional[torch.Tensor] = None):
     """Per-image class tally of ACTIVE rows + integer Fleiss partials.  Rows are SoA device
     tensors (int32, uint8, uint8).  Returns ``(counts int32[n_images,k], partials int64[k+7])``;
-    never synchronises — call :func:`check_tally` on the host copy of ``partials``."""
-    _need_cuda(image_idx, class_idx, active, counts, partials)
+    never synchronises — call :func:`check_tally` on the host copy of ``partials``.
+    ``agree_hist``: optional int64[B2_AGREE_BINS] device tensor receiving the agreement histogram (the
+    general-n kappa from integers, :func:`labels.fleiss_kappa_from_hist`).  ``partials`` may be a view of a
+    larger int64 buffer whose tail is ``agree_hist`` so that ONE all-reduce covers both."""
+    _need_cuda(image_idx, class_idx, active, counts, partials, agree_hist)
     dev = image_idx.device
     init(dev.index)
     rows = image_idx.numel()
@@ -318,7 +324,7 @@ def label_tally_device(image_idx: torch.Tensor, class_idx: torch.Tensor, active:
         partials = torch.empty(k + _lib.B2_PARTIALS_EXTRA, dtype=torch.int64, device=dev)
     flags = _lib.B2_TALLY_SORTED if sorted_by_image else 0
     check(lib.b2_label_tally(_ptr(image_idx), _ptr(class_idx), _ptr(active), rows, image_base, n_images, k, flags,
-                             _ptr(counts), _ptr(partials), None, 0, _stream()))
+                             _ptr(counts), _ptr(partials), _ptr(agree_hist), _stream()))
     return counts, partials
 
 
@@ -350,8 +356,9 @@ def encode_label_rows_device(img_hex: torch.Tensor, opc_uuid: torch.Tensor, ativ
     return image_idx, class_idx, active, unknown
 
 
-def fleiss_partials_device(counts: torch.Tensor, want_sum_pi: bool = False):
-    """Partials (and optionally the float64 sum of per-image agreements P_i) from a count matrix."""
+def fleiss_partials_device(counts: torch.Tensor, want_sum_pi: bool = False, agree_hist: Optional[torch.Tensor] = None):
+    """Partials (and optionally the float64 sum of per-image agreements P_i, and the integer agreement histogram)
+    from a count matrix."""
     _need_cuda(counts)
     dev = counts.device
     init(dev.index)
@@ -364,7 +371,7 @@ def fleiss_partials_device(counts: torch.Tensor, want_sum_pi: bool = False):
         sum_pi = torch.zeros(1, dtype=torch.float64, device=dev)
         ws_bytes = int(lib.b2_fleiss_workspace_bytes(n_images))
         ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.int64, device=dev)
-    check(lib.b2_fleiss_partials(_ptr(counts), n_images, k, _ptr(partials), _ptr(sum_pi), _ptr(ws),
+    check(lib.b2_fleiss_partials(_ptr(counts), n_images, k, _ptr(partials), _ptr(sum_pi), _ptr(agree_hist), _ptr(ws),
                                  ws_bytes, _stream()))
     return partials, sum_pi
 

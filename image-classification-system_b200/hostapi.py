@@ -35,6 +35,24 @@ def init(device: Optional[int] = None) -> int:
     return dev
 
 
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """NumPy array in page-locked host memory (``b2_host_alloc``): copies to and from it are asynchronous and run
+    at full PCIe speed.  Freed when the array (and every view of it) is garbage-collected."""
+    import weakref
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    p = C.c_void_p()
+    check(lib.b2_host_alloc(C.byref(p), max(nbytes, 1)))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    weakref.finalize(buf, lib.b2_host_free, C.c_void_p(p.value))
+    return np.frombuffer(buf, dtype=dt, count=nbytes // dt.itemsize).reshape(shape)
+
+
+def shutdown() -> None:
+    """``b2_shutdown``: release the library's pool of page-locked staging buffers and its cached resize plans."""
+    check(lib.b2_shutdown())
+
+
 def sort_digests(digests: np.ndarray) -> np.ndarray:
     """Sort uint8[m,32] digests in memcmp order (the order ``b2_dedupe`` expects for the table of stored
     digests).  Index maintenance, not on the hot path."""
@@ -118,10 +136,12 @@ def thumbnails(images: Sequence[np.ndarray], out_h: int = 256, out_w: int = 256,
 
 
 def label_tally_host(image_idx, class_idx, active, n_images: int, k: int, sorted_by_image: bool = True,
-                     image_base: int = 0, device: Optional[int] = None, want_counts: bool = True):
+                     image_base: int = 0, device: Optional[int] = None, want_counts: bool = True,
+                     agree_hist: Optional[np.ndarray] = None):
     """Rows in host memory (anything ``np.asarray`` accepts) through ``b2_label_tally_host``: host pointers in,
     ``(counts int32[n_images,k] or None, partials int64[k+7])`` out; raises ``B2Error`` for unsorted rows
-    (sorted mode) or rows out of range."""
+    (sorted mode) or rows out of range.  ``agree_hist``: optional int64[B2_AGREE_BINS] array that receives the
+    agreement histogram (general-n kappa from integers)."""
     dev = init(device)
     img = np.ascontiguousarray(image_idx, dtype=np.int32)
     cls = np.ascontiguousarray(class_idx, dtype=np.uint8)
@@ -131,8 +151,23 @@ def label_tally_host(image_idx, class_idx, active, n_images: int, k: int, sorted
     partials = np.empty(k + _lib.B2_PARTIALS_EXTRA, dtype=np.int64)
     check(lib.b2_label_tally_host(dev, img.ctypes.data, cls.ctypes.data, act.ctypes.data, img.size, image_base,
                                   n_images, k, _lib.B2_TALLY_SORTED if sorted_by_image else 0,
-                                  counts.ctypes.data if counts is not None else None, partials.ctypes.data))
+                                  counts.ctypes.data if counts is not None else None, partials.ctypes.data,
+                                  agree_hist.ctypes.data if agree_hist is not None else None))
     return counts, partials
+
+
+def distinct_images_host(annotator_idx, image_idx, active, n_annotators: int, device: Optional[int] = None) -> np.ndarray:
+    """``b2_distinct_images_host``: rows sorted by (annotator, image) in host memory -> distinct active images
+    per annotator, uint32[n_annotators] (bulk form of routes/classificacoes.py:224-230)."""
+    dev = init(device)
+    a = np.ascontiguousarray(annotator_idx, dtype=np.int32)
+    i = np.ascontiguousarray(image_idx, dtype=np.int32)
+    act = np.ascontiguousarray(active, dtype=np.uint8)
+    assert a.ndim == 1 and i.shape == a.shape and act.shape == a.shape
+    out = np.zeros(n_annotators, dtype=np.uint32)
+    check(lib.b2_distinct_images_host(dev, a.ctypes.data, i.ctypes.data, act.ctypes.data, a.size, n_annotators,
+                                      out.ctypes.data))
+    return out
 
 
 PARTIAL_NAMES = ("S2", "R", "n_rated", "n_pairs_images", "pairs", "rows_seen", "unsorted_pairs")

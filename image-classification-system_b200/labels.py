@@ -42,9 +42,15 @@ class TallyResult:
     n_rated: int                  # images with n_i >= 1
     n_pairs_images: int           # images with n_i >= 2
     pairs: int                    # sum n_i (n_i - 1)
+    agree_hist: Optional[np.ndarray] = None   # int64 [B2_AGREE_BINS]: see fleiss_kappa_from_hist
 
     def kappa(self, n_images: int, n_raters: int) -> float:
+        """Constant-n form: only meaningful when every image has exactly ``n_raters`` active ratings."""
         return fleiss_kappa(self.class_totals, self.S2, self.R, n_images, n_raters)
+
+    def kappa_general(self) -> float:
+        """Variable ratings per image, from the integer agreement histogram of the same pass."""
+        return fleiss_kappa_from_hist(self.class_totals, self.R, self.n_pairs_images, self.agree_hist)
 
 
 def fleiss_kappa(class_totals: Sequence[int], S2: int, R: int, n_images: int, n_raters: int) -> float:
@@ -63,6 +69,25 @@ def fleiss_kappa_general(class_totals: Sequence[int], R: int, sum_pi: float, n_p
     pj = np.asarray(class_totals, dtype=np.float64) / float(int(R))
     p_e = float(np.sum(pj * pj))
     return (p_bar - p_e) / (1.0 - p_e)
+
+
+def sum_pi_from_hist(agree_hist) -> float:
+    """sum_i P_i over images with n_i >= 2 from the agreement histogram of ``b2_label_tally``: bin n holds
+    sum (sum_j n_ij^2 - n_i) over the images with n_i = n, so sum_i P_i = sum_n bin[n] / (n (n - 1)) — float64 from
+    integers in a fixed order (ascending n): bit-identical for any sharding once the bins are all-reduced.  Raises
+    when images with >= B2_AGREE_BINS ratings exist (bin 0): use ``engine.fleiss_partials_device(want_sum_pi=True)``."""
+    h = np.asarray(agree_hist, dtype=np.int64)
+    if int(h[0]) != 0:
+        raise ValueError(f"{int(h[0])} images have >= {h.shape[0]} ratings: the histogram does not cover them")
+    total = 0.0
+    for n in np.nonzero(h[2:])[0] + 2:
+        total += float(int(h[n])) / float(int(n) * (int(n) - 1))
+    return total
+
+
+def fleiss_kappa_from_hist(class_totals: Sequence[int], R: int, n_pairs_images: int, agree_hist) -> float:
+    """General-n Fleiss kappa (P_bar = mean of P_i over images with n_i >= 2) from integers only."""
+    return fleiss_kappa_general(class_totals, R, sum_pi_from_hist(agree_hist), n_pairs_images)
 
 
 def _rows_to_device(image_idx, class_idx, active, device):
@@ -89,18 +114,25 @@ def label_tally(image_idx, class_idx, active, n_images: int, k: int, sorted_by_i
             sorted_by_image = bool(np.all(image_idx[1:] >= image_idx[:-1])) if image_idx.size else True
         else:
             sorted_by_image = True
+    from ._lib import B2_AGREE_BINS
     if not any(_is_tensor(a) for a in (image_idx, class_idx, active)):
         # host rows: one native call with host pointers (b2_label_tally_host stages, tallies, reads back, checks)
-        counts, p = label_tally_host(image_idx, class_idx, active, n_images, k, sorted_by_image, image_base, device)
+        hist = np.zeros(B2_AGREE_BINS, dtype=np.int64)
+        counts, p = label_tally_host(image_idx, class_idx, active, n_images, k, sorted_by_image, image_base, device,
+                                     agree_hist=hist)
     else:
+        import torch
         d_img, d_cls, d_act = _rows_to_device(image_idx, class_idx, active, device)
-        d_counts, partials = _engine().label_tally_device(d_img, d_cls, d_act, n_images, k, image_base, sorted_by_image)
+        d_hist = torch.empty(B2_AGREE_BINS, dtype=torch.int64, device=d_img.device)
+        d_counts, partials = _engine().label_tally_device(d_img, d_cls, d_act, n_images, k, image_base, sorted_by_image,
+                                                          agree_hist=d_hist)
         p = partials.cpu().numpy()
         hostapi.check_tally(p, k, d_img.numel())
         counts = d_counts.cpu().numpy()
+        hist = d_hist.cpu().numpy()
     d = hostapi.partials_dict(p, k)
     return TallyResult(counts=counts, class_totals=d["class_totals"], S2=d["S2"], R=d["R"],
-                       n_rated=d["n_rated"], n_pairs_images=d["n_pairs_images"], pairs=d["pairs"])
+                       n_rated=d["n_rated"], n_pairs_images=d["n_pairs_images"], pairs=d["pairs"], agree_hist=hist)
 
 
 label_tally_host = hostapi.label_tally_host
@@ -114,13 +146,8 @@ def distinct_images_per_annotator(annotator_idx, image_idx, active, n_annotators
     i = np.ascontiguousarray(image_idx, dtype=np.int32)
     act = np.ascontiguousarray(active, dtype=np.uint8)
     order = np.lexsort((i, a))
-    import torch
-    engine = _engine()
-    dev = torch.device("cuda", engine.init(device))
-    out = engine.distinct_images_per_annotator_device(
-        torch.from_numpy(a[order]).to(dev), torch.from_numpy(i[order]).to(dev),
-        torch.from_numpy(act[order]).to(dev), n_annotators)
-    return out.cpu().numpy()
+    # host rows: one native call with host pointers (no PyTorch needed — the crud mirror runs where it is absent)
+    return hostapi.distinct_images_host(a[order], i[order], act[order], n_annotators, device).astype(np.int32)
 
 
 class LabelEncoder:

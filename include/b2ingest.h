@@ -12,10 +12,10 @@
  *     work is enqueued on it and the call returns without synchronising unless stated.
  *   - Re-entrant: the device-pointer entry points keep no global mutable state except immutable
  *     per-shape coefficient tables owned by b2_resize_plan objects; the host-pointer entry points
- *     (b2_*_host, b2_ingest_stream_*) share a mutex-guarded pool of page-locked staging buffers and a
+ *     (b2_*_host, b2_ingest_ring_*) share a mutex-guarded pool of page-locked staging buffers and a
  *     cache of resize plans.  Several host threads may call concurrently (the reference reaches this
- *     path from up to five service threads); a b2_ingest_stream belongs to
- *     one thread at a time.
+ *     path from up to five service threads); a b2_ingest_ring or a b2_comm belongs
+ *     to one thread at a time.
  *   - There is no CPU fallback.  Without a Blackwell GPU every compute entry point fails.
  *
  * Each entry point cites the reference interface (file:line under the reference repo) it
@@ -37,14 +37,19 @@ typedef enum b2_status {
     B2_ERR_CUDA = -2,         /* a CUDA runtime call failed; see b2_last_error()              */
     B2_ERR_NOT_SORTED = -3,   /* b2_label_tally_status: rows out of image order in sorted mode */
     B2_ERR_NO_DEVICE = -4,    /* no CUDA device / not compute capability 10.x                */
-    B2_ERR_WORKSPACE = -5     /* workspace smaller than the matching *_workspace_bytes()      */
+    B2_ERR_WORKSPACE = -5,    /* workspace smaller than the matching *_workspace_bytes()      */
+    B2_ERR_NCCL = -6          /* NCCL missing in the process or a collective failed            */
 } b2_status;
 
 /* ---- library ------------------------------------------------------------------------- */
-int b2_version(void);                       /* ABI version, currently 1                       */
+int b2_version(void);                       /* ABI version, currently 2                       */
 const char *b2_last_error(void);            /* thread-local, never NULL                        */
 int b2_init(int device);                    /* cudaSetDevice + capability check (sm_100)       */
 int b2_device_sm_count(int device, int *sm_count);
+/* Release what the host-pointer entry points keep between calls (pool of page-locked staging buffers, cached resize
+ * plans).  Objects the caller created (plans, rings, communicators) are destroyed by the caller first; no other call
+ * may be in flight.  The library stays usable: everything is re-created on demand. */
+int b2_shutdown(void);
 
 /* ---- a1: content hash -------------------------------------------------------------------
  * Replaces hashlib.sha256(data).hexdigest() at app/services/webdav_sync.py:59 (called :445),
@@ -76,7 +81,7 @@ int b2_digest_hex(const uint8_t *d_digests, uint32_t n, char *d_hex, void *strea
  *   d_seq (NULL = i): arrival order; "first occurrence" = smallest seq (multi-GPU callers
  *       pass the global image index after the all-gather).
  * Outputs: d_is_new[i] = 1 iff i is the first valid occurrence of its digest and the digest
- * is not in d_existing (the insert branch); d_first_index[i] / d_last_index[i] (may be NULL)
+ * is not in d_existing (the insert branch); d_first_index[i] / d_last_index[i] (each may be NULL)
  * = batch index of the first / last valid occurrence of the same digest (identity columns
  * come from the first, nome_img/caminho_img from the last); d_counts[3] =
  * {processed, created, updated}.  d_workspace: b2_dedupe_workspace_bytes(n) bytes.
@@ -114,15 +119,6 @@ int b2_resize_normalize_batch(const b2_resize_plan *plan, const uint8_t *d_rgb,
                               const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,
                               uint8_t *d_thumb, float *d_preview,
                               const float mean[3], const float inv_std[3], void *stream);
-/* Same with flags.  B2_RESIZE_BESIDE_HASH: the caller runs b2_sha256_batch on another stream at the same
- * time.  It used to select a horizontal pass that left the INT32 ALU pipe to the hash; the kernel's single
- * pass is now the faster one in both situations, so the flag is accepted and changes nothing. */
-#define B2_RESIZE_BESIDE_HASH 1u
-int b2_resize_normalize_batch_ex(const b2_resize_plan *plan, const uint8_t *d_rgb,
-                                 const uint64_t *d_offsets, const uint32_t *d_out_slot, uint32_t n,
-                                 uint8_t *d_thumb, float *d_preview,
-                                 const float mean[3], const float inv_std[3], uint32_t flags, void *stream);
-
 /* ---- a13: per-image label tally + Fleiss partials ---------------------------------------
  * Absent in the reference (it only groups one user's rows, app/crud/classificacao_crud.py:
  * 318-322); required by BASELINE.json configs 1,4,5.  Rows are SoA (image_idx int32,
@@ -142,23 +138,28 @@ int b2_resize_normalize_batch_ex(const b2_resize_plan *plan, const uint8_t *d_rg
  * The call never synchronises.  Once the partials are on the host, b2_label_tally_status()
  * turns the last two entries into B2_OK / B2_ERR_NOT_SORTED / B2_ERR_BAD_ARG (a row with
  * image_idx or class_idx out of range); on error d_counts is unspecified.
- * Row arrays must be 16-byte aligned.  No workspace is needed (pass NULL, 0).
+ * d_agree_hist (may be NULL): int64[B2_AGREE_BINS], zeroed by the call — the general-n Fleiss kappa without a
+ *   second pass over the count matrix and still exact for any sharding: bin n (2 <= n < B2_AGREE_BINS) =
+ *   sum over the images with n_i = n of (sum_j n_ij^2 - n_i), so that sum_i P_i = sum_n bin[n] / (n (n - 1)) is
+ *   computed on the host from integers (after the same integer all-reduce as the partials); bin 0 = images with
+ *   n_i >= B2_AGREE_BINS (general kappa then needs b2_fleiss_partials' d_sum_pi), bin 1 = 0.
+ * Row arrays must be 16-byte aligned.
  */
 #define B2_TALLY_SORTED 1u
 #define B2_PARTIALS_EXTRA 7
-uint64_t b2_label_tally_workspace_bytes(uint32_t n_images);
+#define B2_AGREE_BINS 1024
 int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
                    uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
-                   int32_t *d_counts, int64_t *d_partials,
-                   void *d_workspace, uint64_t workspace_bytes, void *stream);
+                   int32_t *d_counts, int64_t *d_partials, int64_t *d_agree_hist, void *stream);
 int b2_label_tally_status(const int64_t *h_partials, uint32_t k, uint64_t rows);   /* host only */
 /* Partials from an existing count matrix (e.g. after a row-sharded all-reduce of counts); the
  * last two entries stay 0.  d_sum_pi (may be NULL): sum over images with n_i >= 2 of
  * (sum_j n_ij^2 - n_i)/(n_i(n_i-1)), float64, reduced in a fixed order (reproducible for a given
- * n_images, k); needs b2_fleiss_workspace_bytes() of 8-byte aligned workspace. */
+ * n_images, k); needs b2_fleiss_workspace_bytes() of 8-byte aligned workspace.  d_agree_hist (may be NULL): as
+ * in b2_label_tally. */
 uint64_t b2_fleiss_workspace_bytes(uint32_t n_images);
 int b2_fleiss_partials(const int32_t *d_counts, uint32_t n_images, uint32_t k,
-                       int64_t *d_partials, double *d_sum_pi,
+                       int64_t *d_partials, double *d_sum_pi, int64_t *d_agree_hist,
                        void *d_workspace, uint64_t workspace_bytes, void *stream);
 
 /* ---- next row (f3): per-user aggregation ---------------------------------------------------
@@ -189,31 +190,51 @@ int b2_encode_label_rows(const char *d_img_hex, const uint8_t *d_opc_uuid, const
  * `classificacoes`.  These entry points take host pointers only and own the device side (staging
  * buffers, streams, events), so a caller needs nothing but an FFI.  Page-locked buffers
  * (b2_host_alloc, or any pinned allocation) make the copies asynchronous and full speed; pageable
- * memory works, slower.
- *
- * b2_ingest_stream: fixed-shape batches of n <= max_images decoded RGB images (HWC, packed back to
- * back, in_h*in_w*3 a multiple of 16) -> 32-byte digests, the dedupe decision of b2_dedupe against
- * the sorted table h_existing_sorted (m digests, may be NULL/0) and its {processed, created, updated}
- * counts, uint8 HWC thumbnails and (optional) float32 CHW previews, all in host memory.  The batch is
- * copied in chunks of chunk_images on one stream; each chunk's hash and resize run on their own
- * streams beside the remaining copies and their results are read back while later chunks arrive.
- * submit() only enqueues work and returns; the output buffers are complete when wait() returns
- * (it also reports the bytes copied each way and the kernels launched).  One batch per stream at a
- * time; two streams used alternately keep two batches in flight.  h_first_index / h_last_index /
- * h_previews may be NULL. */
-typedef struct b2_ingest_stream b2_ingest_stream;
+ * memory works, slower. */
 int b2_host_alloc(void **p, uint64_t bytes);
 int b2_host_free(void *p);
-int b2_ingest_stream_create(int device, int in_h, int in_w, int out_h, int out_w, uint32_t max_images,
-                            uint32_t chunk_images, int want_preview, b2_ingest_stream **stream_out);
-int b2_ingest_stream_destroy(b2_ingest_stream *s);
-int b2_ingest_stream_submit(b2_ingest_stream *s, const uint8_t *h_images, uint32_t n,
-                            const uint8_t *h_existing_sorted, uint64_t m,
-                            uint8_t *h_digests, uint8_t *h_is_new, int32_t *h_first_index,
-                            int32_t *h_last_index, uint32_t *h_counts /*3*/,
-                            uint8_t *h_thumbs, float *h_previews);
-int b2_ingest_stream_wait(b2_ingest_stream *s, uint64_t *h2d_bytes, uint64_t *d2h_bytes,
-                          uint32_t *kernel_launches);
+
+/* b2_ingest_ring: the streaming form of the whole ingest step for LISTINGS of any mix of image sizes — what the
+ * reference's sync loop holds after its downloads (webdav_sync.py:273-283, :441; BASELINE configs 2, 3, 5).
+ * Depth is bounded in BYTES: one device staging ring of `ring_bytes` is carved first-in first-out into chunks of
+ * consecutive listing entries (about `chunk_bytes` each, 0 = 1 GiB; smaller for small listings) holding
+ * [metadata | images | thumbnails | previews]; a chunk is released when its hash kernel, its resize kernels and
+ * the read-back of its outputs are done, and submit() blocks only while the ring is full.  SHA-256 is serial per
+ * message (~60 MB/s per message whatever the batch), so PCIe is only kept busy with >= ~1 000 messages hashing at
+ * once: size the ring at a second's worth of input (tens of GB) and keep several listings in flight.
+ *
+ * submit(): entry i of the listing is
+ *     h_pixels[i] -> h_hw[2i] x h_hw[2i+1] x 3 bytes of decoded RGB (HWC); NULL pointer or a zero dimension = no
+ *                    thumbnail for this entry (its output slots are zeroed if the chunk has other thumbnails,
+ *                    else untouched).  h_pixels may be NULL altogether (hash + dedupe only).
+ *     h_files[i]  -> h_file_lens[i] bytes = the message that is hashed (the downloaded file).  h_files == NULL:
+ *                    the pixel buffer is the message (BASELINE's synthetic images).
+ *     h_valid[i]  == 0 (h_valid may be NULL = all valid): skipped before the lookup (webdav_sync.py:314, :320) —
+ *                    not copied, not counted, is_new = 0, first/last index = -1.
+ * Outputs, all in host memory and in LISTING ORDER, complete when wait(ticket) returns: h_digests (n x 32),
+ * h_is_new (n), h_first_index / h_last_index (n each, may be NULL), h_counts[3] = {processed, created, updated}
+ * of b2_dedupe over the listing against h_existing_sorted (m digests in memcmp order, may be NULL / 0),
+ * h_thumbs (n x out_h*out_w*3, uint8 HWC; NULL only when h_pixels is NULL), h_previews (n x 3*out_h*out_w float32
+ * CHW, may be NULL).  Input and output buffers must stay valid until wait() returns; page-locked buffers make every
+ * copy asynchronous.  Up to max_listings listings in flight; tickets may be waited for in any order.
+ * poll(): *done = 1 when wait() would not block; *images_flushed (may be NULL) = leading entries of the listing
+ * whose thumbnails / previews are already in the host buffers (a consumer can start on them).
+ * A ring belongs to one thread at a time.  On any error inside submit() everything the ring had in flight is
+ * drained before the call returns, so no copy still references the caller's buffers. */
+typedef struct b2_ingest_ring b2_ingest_ring;
+int b2_ingest_ring_create(int device, uint64_t ring_bytes, uint64_t chunk_bytes, uint32_t max_listings,
+                          int out_h, int out_w, int want_preview, b2_ingest_ring **ring_out);
+int b2_ingest_ring_destroy(b2_ingest_ring *r);
+int b2_ingest_ring_submit(b2_ingest_ring *r, const uint8_t *const *h_pixels, const uint32_t *h_hw,
+                          const uint8_t *const *h_files, const uint64_t *h_file_lens, const uint8_t *h_valid,
+                          uint32_t n, const uint8_t *h_existing_sorted, uint64_t m,
+                          uint8_t *h_digests, uint8_t *h_is_new, int32_t *h_first_index, int32_t *h_last_index,
+                          uint32_t *h_counts /*3*/, uint8_t *h_thumbs, float *h_previews, uint64_t *ticket);
+int b2_ingest_ring_wait(b2_ingest_ring *r, uint64_t ticket, uint64_t *h2d_bytes, uint64_t *d2h_bytes,
+                        uint32_t *kernel_launches);
+int b2_ingest_ring_poll(b2_ingest_ring *r, uint64_t ticket, int *done, uint32_t *images_flushed);
+int b2_ingest_ring_stats(const b2_ingest_ring *r, uint64_t *ring_bytes, uint64_t *bytes_in_flight,
+                         uint32_t *chunks_in_flight, uint64_t *stalls);
 /* SHA-256 of n byte strings anywhere in host memory (h_msgs[i] -> h_lens[i] bytes: e.g. the buffers of the
  * downloaded files, webdav_sync.py:441-445): packed into a recycled page-locked buffer, one copy, one kernel,
  * digests (n*32) and optionally their lowercase hex form (n*64, no terminator) back.  Blocking. */
@@ -233,7 +254,44 @@ int b2_thumbnails_host(int device, const uint8_t *const *h_rgb, const uint32_t *
  * matrix h_counts (int32[n_images * k]).  Blocking; returns the verdict of b2_label_tally_status. */
 int b2_label_tally_host(int device, const int32_t *h_image_idx, const uint8_t *h_class_idx,
                         const uint8_t *h_active, uint64_t rows, uint32_t image_base, uint32_t n_images,
-                        uint32_t k, uint32_t flags, int32_t *h_counts, int64_t *h_partials);
+                        uint32_t k, uint32_t flags, int32_t *h_counts, int64_t *h_partials,
+                        int64_t *h_agree_hist /* NULL or int64[B2_AGREE_BINS] */);
+/* b2_distinct_images_per_annotator for rows (sorted by (annotator, image)) in host memory.  Blocking. */
+int b2_distinct_images_host(int device, const int32_t *h_annotator_idx, const int32_t *h_image_idx,
+                            const uint8_t *h_active, uint64_t rows, uint32_t n_annotators, uint32_t *h_distinct);
+
+/* ---- (e) multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch -----------------------------------------
+ * SURVEY.md section 8(e).  Images and label rows shard with no data-path collective; the two exchanges are an
+ * all-gather of digests for the cross-rank dedupe decision and an integer all-reduce of the label partials.  NCCL is
+ * bound at run time (the copy already loaded in the process, else libnccl.so.2, else $B2_NCCL_LIB); without it these
+ * return B2_ERR_NCCL.  b2_comm_unique_id() is called on ONE rank, its 128 bytes travel to the others by whatever the
+ * host has (file, socket, torch.distributed store), then every rank calls b2_comm_init (collective, blocking).
+ * Collectives are enqueued on the caller's stream and return without synchronising. */
+#define B2_COMM_ID_BYTES 128
+typedef struct b2_comm b2_comm;
+int b2_comm_unique_id(uint8_t *id_out /*B2_COMM_ID_BYTES*/);
+int b2_comm_init(int device, int rank, int world, const uint8_t *id /*B2_COMM_ID_BYTES*/, b2_comm **comm_out);
+int b2_comm_destroy(b2_comm *c);
+int b2_comm_info(const b2_comm *c, int *rank, int *world, int *nccl_version);
+/* d_all (world x n_per_rank x 32) = every rank's d_local (n_per_rank x 32) in rank order (ncclAllGather). */
+int b2_allgather_digests(b2_comm *c, const uint8_t *d_local, uint32_t n_per_rank, uint8_t *d_all, void *stream);
+/* In-place sum over ranks of count int64 values: class totals + partials (+ agreement histogram) of b2_label_tally
+ * (ncclAllReduce, ncclInt64, ncclSum).  kappa computed from the result is bit-identical for any GPU count. */
+int b2_allreduce_i64(b2_comm *c, int64_t *d_values, uint64_t count, void *stream);
+/* The dedupe decision of WebDAVSync._process_image_batch (webdav_sync.py:311-400) for a listing SHARDED over the
+ * ranks in any way (dist.shard_by_bytes for mixed sizes): rank r holds n_local digests, their global listing
+ * positions d_seq (unique over all ranks) and optional validity flags; n_max = the largest n_local of any rank.
+ * Shards are padded to n_max with invalid entries, digests / positions / flags are all-gathered in one NCCL group
+ * and every rank runs the same b2_dedupe keyed on the listing position, so "first seen wins" means first in the
+ * LISTING whatever rank holds it.  Outputs for this rank's entries: d_is_new, d_first_seq / d_last_seq (may be NULL)
+ * = listing position of the first / last occurrence of the same content (-1 = invalid entry); d_counts[3] =
+ * {processed, created, updated} of the WHOLE listing (identical on every rank).  d_workspace: 256-byte aligned,
+ * b2_dedupe_global_workspace_bytes(world, n_max) bytes. */
+uint64_t b2_dedupe_global_workspace_bytes(uint32_t world, uint32_t n_max);
+int b2_dedupe_global(b2_comm *c, const uint8_t *d_digests, const uint8_t *d_valid, const uint32_t *d_seq,
+                     uint32_t n_local, uint32_t n_max, const uint8_t *d_existing, uint64_t m,
+                     uint8_t *d_is_new, int64_t *d_first_seq, int64_t *d_last_seq, uint32_t *d_counts /*3*/,
+                     void *d_workspace, uint64_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,7 @@ from .labels import (  # noqa: F401
     fleiss_partials,
     fleiss_kappa,
     fleiss_kappa_general,
+    agreement_hist,
     group_by_image,
     distinct_image_count,
     history_grouping,

@@ -86,6 +86,20 @@ def fleiss_kappa_general(counts: np.ndarray) -> float:
     return (p_bar - p_e) / (1.0 - p_e)
 
 
+def agreement_hist(counts: np.ndarray, bins: int = 1024) -> np.ndarray:
+    """The integer form of sum_i P_i the product accumulates in its tally pass: bin n (2 <= n < bins) =
+    sum over images with n_i = n of (sum_j n_ij^2 - n_i); bin 0 = images with n_i >= bins; bin 1 = 0.
+    Graft-defined (general-n kappa without a second pass, exact under sharding)."""
+    c = counts.astype(np.int64)
+    n_i = c.sum(axis=1)
+    num = (c * c).sum(axis=1) - n_i
+    h = np.zeros(bins, dtype=np.int64)
+    m = (n_i >= 2) & (n_i < bins)
+    np.add.at(h, n_i[m], num[m])
+    h[0] = int((n_i >= bins).sum())
+    return h
+
+
 # ------------------------------------------------------------------ (1) per-user paths
 def group_by_image(rows: Sequence[Dict], id_con, content_hashes: Sequence[str]) -> Dict[str, List[Dict]]:
     """classificacao_crud.py:305-324.  ``rows`` = the ``classificacoes`` table in storage

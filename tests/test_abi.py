@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_binding_covers_header():
     from ics_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
-    assert _lib.lib.b2_version() == 1
+    assert _lib.lib.b2_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

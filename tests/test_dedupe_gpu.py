@@ -129,3 +129,20 @@ def test_config3_scale_two_million_digests_with_existing_table():
     want_new = (first_of[src] == np.arange(n)) & ~stored[src]
     assert np.array_equal(is_new, want_new)
     assert counts.cpu().tolist() == [n, int(want_new.sum()), n - int(want_new.sum())]
+
+
+def test_first_and_last_index_are_optional():
+    """include/b2ingest.h: d_first_index / d_last_index may each be NULL."""
+    import ctypes as C
+
+    from ics_b200._lib import check, lib
+    rng = np.random.default_rng(2)
+    base = rng.integers(0, 256, size=(40, 32), dtype=np.uint8)
+    dig = torch.from_numpy(base[rng.integers(0, 40, 300)]).cuda()
+    is_new, first, last, counts = engine.dedupe_device(dig)
+    new2 = torch.empty_like(is_new)
+    counts2 = torch.empty_like(counts)
+    ws = torch.empty(int(lib.b2_dedupe_workspace_bytes(300)) // 8, dtype=torch.int64, device="cuda")
+    check(lib.b2_dedupe(dig.data_ptr(), None, None, 300, None, C.c_uint64(0), new2.data_ptr(), None, None, counts2.data_ptr(),
+                        ws.data_ptr(), ws.numel() * 8, torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(new2, is_new) and torch.equal(counts2, counts)

@@ -53,23 +53,34 @@ def test_label_tally_host_zero_rows_and_unsorted_mode():
     assert np.array_equal(counts, label_tally(img, cls, act, 40, 6)) and int(partials[6 + 1]) == int(act.sum())
 
 
-def test_ingest_stream_error_returns():
+def test_ingest_ring_error_returns():
     lib = C.CDLL(ics_b200.LIB_PATH)
     lib.b2_last_error.restype = C.c_char_p
-    st = C.c_void_p()
-    assert lib.b2_ingest_stream_create(0, 5, 5, 8, 8, 4, 2, 0, C.byref(st)) == -1          # 75 bytes per image: not 16-aligned
-    assert b"multiple of 16" in lib.b2_last_error()
-    assert lib.b2_ingest_stream_create(0, 8, 8, 8, 8, 0, 2, 0, C.byref(st)) == -1          # empty batch capacity
-    assert lib.b2_ingest_stream_create(0, 8, 8, 8, 8, 4, 2, 0, C.byref(st)) == 0
-    assert lib.b2_ingest_stream_wait(st, None, None, None) == -1                           # nothing submitted
-    buf = (C.c_uint8 * (5 * 192))()
-    dig, new, cnt, th = (C.c_uint8 * 160)(), (C.c_uint8 * 5)(), (C.c_uint32 * 4)(), (C.c_uint8 * (5 * 192))()
-    assert lib.b2_ingest_stream_submit(st, buf, 5, None, C.c_uint64(0), dig, new, None, None, cnt, th, None) == -1   # n > max
-    prev = (C.c_float * (4 * 192))()
-    assert lib.b2_ingest_stream_submit(st, buf, 4, None, C.c_uint64(0), dig, new, None, None, cnt, th, prev) == -1   # no previews
-    assert lib.b2_ingest_stream_submit(st, buf, 4, None, C.c_uint64(0), dig, new, None, None, cnt, th, None) == 0    # pageable memory works
-    assert lib.b2_ingest_stream_wait(st, None, None, None) == 0
-    assert list(cnt)[:3] == [4, 1, 3] and list(new) [:4] == [1, 0, 0, 0]                   # four identical (zero) images
-    assert bytes(dig[:32]).hex() == hashlib.sha256(bytes(192)).hexdigest()
-    assert lib.b2_ingest_stream_destroy(st) == 0
-    assert lib.b2_ingest_stream_destroy(None) == 0
+    u64 = C.c_uint64
+    ring, ticket = C.c_void_p(), u64()
+    assert lib.b2_ingest_ring_create(0, u64(1 << 20), u64(0), 2, 8, 8, 0, C.byref(ring)) == -1       # ring below 64 MiB
+    assert b"64 MiB" in lib.b2_last_error()
+    assert lib.b2_ingest_ring_create(0, u64(64 << 20), u64(0), 0, 8, 8, 0, C.byref(ring)) == -1      # no listing slot
+    assert lib.b2_ingest_ring_create(0, u64(64 << 20), u64(0), 1, 8, 8, 0, C.byref(ring)) == 0
+    assert lib.b2_ingest_ring_wait(ring, u64(1), None, None, None) == -1                             # nothing submitted
+    n = 4
+    buf = (C.c_uint8 * (n * 75))()                                                                   # 5x5x3 = 75 bytes: not 16-byte multiples
+    ptrs = (C.c_void_p * n)(*[C.addressof(buf) + 75 * i for i in range(n)])
+    hw = (C.c_uint32 * (2 * n))(*([5, 5] * n))
+    dig, new, cnt, th = (C.c_uint8 * (32 * n))(), (C.c_uint8 * n)(), (C.c_uint32 * 4)(), (C.c_uint8 * (n * 192))()
+    prev = (C.c_float * (n * 192))()
+    assert lib.b2_ingest_ring_submit(ring, ptrs, hw, None, None, None, 0, None, u64(0), dig, new, None, None, cnt, th, None,
+                                     C.byref(ticket)) == -1                                          # empty listing
+    assert lib.b2_ingest_ring_submit(ring, ptrs, hw, None, None, None, n, None, u64(0), dig, new, None, None, cnt, th, prev,
+                                     C.byref(ticket)) == -1                                          # no previews in this ring
+    assert lib.b2_ingest_ring_submit(ring, ptrs, hw, None, None, None, n, None, u64(0), dig, new, None, None, cnt, None, None,
+                                     C.byref(ticket)) == -1                                          # pixels but no thumbnail buffer
+    assert lib.b2_ingest_ring_submit(ring, ptrs, hw, None, None, None, n, None, u64(0), dig, new, None, None, cnt, th, None,
+                                     C.byref(ticket)) == 0, lib.b2_last_error()                      # pageable memory, odd sizes: works
+    assert lib.b2_ingest_ring_submit(ring, ptrs, hw, None, None, None, n, None, u64(0), dig, new, None, None, cnt, th, None,
+                                     C.byref(u64())) == -1                                           # the only slot is taken
+    assert lib.b2_ingest_ring_wait(ring, ticket, None, None, None) == 0
+    assert list(cnt)[:3] == [4, 1, 3] and list(new)[:4] == [1, 0, 0, 0]                              # four identical (zero) images
+    assert bytes(dig[:32]).hex() == hashlib.sha256(bytes(75)).hexdigest()
+    assert lib.b2_ingest_ring_destroy(ring) == 0
+    assert lib.b2_ingest_ring_destroy(None) == 0

@@ -62,6 +62,23 @@ assert p is None and np.array_equal(t[1], thumbnail_u8(imgs[1], 100, 60))
 img, cls, act = synth_label_rows(1000, 50, 10)
 tally = ics_b200.label_tally(img, cls, act, 1000, 50)
 assert np.array_equal(tally.counts, label_tally(img, cls, act, 1000, 50))
+assert abs(tally.kappa_general()) < 1.0
+# bulk distinct-image counts (crud mirror) and the streaming ring, both without PyTorch
+import uuid
+users = [str(uuid.UUID(int=c + 1)) for c in range(4)]
+class Db:
+    classificacoes = [{"id_con": u, "id_img": "%064x" % (i % 5), "id_opc": "o", "ativo": (i + c) % 3 != 0}
+                      for c, u in enumerate(users) for i in range(9)]
+got = classificacao_crud.contagem_classificacoes_todos(Db())
+for u in users:
+    assert got[u] == len({r["id_img"] for r in Db.classificacoes if r["id_con"] == u and r["ativo"]}), (u, got)
+from ics_b200.pipeline import IngestRing
+ring = IngestRing(ring_bytes=64 << 20, max_listings=2, max_images=8, out_h=256, out_w=256)
+res = ring.result(ring.submit(imgs))
+assert [bytes(d).hex() for d in res.digests] == hashes[:6]
+assert np.array_equal(res.thumbs[4], thumbnail_u8(imgs[4], 256, 256))
+assert res.stats == {"processed": 6, "created": 5, "updated": 1}
+ring.close()
 loaded = [m for m, v in sys.modules.items() if v is not None and (m == "torch" or m.startswith("torch."))]
 assert not loaded, loaded
 print("OK")

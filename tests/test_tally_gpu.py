@@ -227,3 +227,82 @@ def test_distinct_images_per_annotator(ref_labels):
     for case in ref_labels["distinct_count"]:
         if case["id_con"] is not None:
             assert got[case["id_con"]] == case["total"]
+
+
+def test_distinct_images_long_inactive_runs_and_host_entry():
+    """Runs of one (annotator, image) pair with thousands of rows, active ones at the start, the end, or nowhere:
+    a run counts once iff it holds an active row (the kernel scans each run forward once: linear)."""
+    from ics_b200 import hostapi
+    rng = np.random.default_rng(12)
+    ann, img, act = [], [], []
+    want = np.zeros(7, dtype=np.int64)
+    for a in range(7):
+        for i in range(int(rng.integers(1, 9))):
+            length = int(rng.choice([1, 2, 33, 700, 5000]))
+            flags = np.zeros(length, dtype=np.uint8)
+            mode = int(rng.integers(0, 4))
+            if mode == 1:
+                flags[0] = 1
+            elif mode == 2:
+                flags[-1] = 1
+            elif mode == 3:
+                flags[rng.integers(0, length, size=max(1, length // 3))] = 1
+            ann += [a] * length
+            img += [i * 3] * length
+            act.append(flags)
+            want[a] += int(flags.any())
+    ann, img, act = np.array(ann, np.int32), np.array(img, np.int32), np.concatenate(act)
+    got = hostapi.distinct_images_host(ann, img, act, 7)
+    assert got.tolist() == want.tolist()
+    got_d = engine.distinct_images_per_annotator_device(torch.from_numpy(ann).cuda(), torch.from_numpy(img).cuda(),
+                                                        torch.from_numpy(act).cuda(), 7)
+    assert got_d.cpu().tolist() == want.tolist()
+
+
+@pytest.mark.parametrize("sorted_rows", [True, False])
+def test_agreement_histogram_gives_general_kappa_from_integers(sorted_rows):
+    """Variable ratings per image (active w.p. 0.8, some images empty or single-rated): the histogram of the tally
+    pass equals the oracle's bit for bit and the kappa computed from it matches the count-matrix formula to 1e-12;
+    shards add up exactly, so the general kappa is identical for any GPU count too."""
+    from oracle import agreement_hist
+    from ics_b200.dist import shard_rows_by_image
+    n_images, k = 30_011, 50
+    rng = np.random.default_rng(9)
+    per = rng.integers(0, 40, n_images)
+    per[::97] = 1
+    img = np.repeat(np.arange(n_images, dtype=np.int32), per)
+    cls = rng.integers(0, k, img.size).astype(np.uint8)
+    cls[rng.random(img.size) < 0.5] = 3
+    act = (rng.random(img.size) < 0.8).astype(np.uint8)
+    if not sorted_rows:
+        perm = rng.permutation(img.size)
+        img_in, cls_in, act_in = img[perm], cls[perm], act[perm]
+    else:
+        img_in, cls_in, act_in = img, cls, act
+    t = labels.label_tally(img_in, cls_in, act_in, n_images, k, sorted_by_image=sorted_rows)
+    counts = label_tally(img, cls, act, n_images, k)
+    assert np.array_equal(t.counts, counts)
+    assert np.array_equal(t.agree_hist, agreement_hist(counts))
+    kg = t.kappa_general()
+    assert abs(kg - fleiss_kappa_general(counts)) <= 1e-12 * abs(kg)
+    if sorted_rows:
+        tot = np.zeros_like(t.agree_hist)
+        for r in range(3):
+            lo, hi, r0, r1 = shard_rows_by_image(img, n_images, r, 3)
+            tot += labels.label_tally(img[r0:r1], cls[r0:r1], act[r0:r1], hi - lo, k, image_base=lo).agree_hist
+        assert np.array_equal(tot, t.agree_hist)
+    # device-pointer form + the count-matrix form agree with it
+    d_counts = torch.from_numpy(counts).cuda()
+    hist = torch.empty(1024, dtype=torch.int64, device="cuda")
+    engine.fleiss_partials_device(d_counts, agree_hist=hist)
+    assert np.array_equal(hist.cpu().numpy(), t.agree_hist)
+
+
+def test_agreement_histogram_overflow_bin():
+    """Images with >= B2_AGREE_BINS ratings are counted in bin 0 and kappa_general refuses to answer."""
+    img = np.concatenate([np.zeros(1500, np.int32), np.ones(10, np.int32)])
+    cls = (np.arange(img.size) % 4).astype(np.uint8)
+    t = labels.label_tally(img, cls, np.ones(img.size, np.uint8), 2, 4)
+    assert int(t.agree_hist[0]) == 1 and int(t.agree_hist[10]) == 2 * 3 * 3 + 2 * 2 * 2 - 10
+    with pytest.raises(ValueError):
+        t.kappa_general()

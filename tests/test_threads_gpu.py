@@ -28,7 +28,7 @@ def _worker(tid: int, rounds: int, errors: list):
         img, cls, act = synth_label_rows(n_img, k, 9 + tid)
         want_counts = label_tally(img, cls, act, n_img, k)
         pipe = None
-        if (shape[0] * shape[1] * 3) % 16 == 0:
+        if True:                                            # any shape: the ring pads image starts itself
             pipe = IngestPipeline(shape[0], shape[1], len(images), chunk_images=4)
             host = torch.empty((len(images), shape[0] * shape[1] * 3), dtype=torch.uint8, pin_memory=True)
             host.copy_(torch.from_numpy(np.stack([im.reshape(-1) for im in images])))
@@ -46,8 +46,8 @@ def _worker(tid: int, rounds: int, errors: list):
             assert np.array_equal(c2.cpu().numpy(), want_counts)
             if pipe is not None:
                 r = pipe.run(host)
-                assert [bytes(x).hex() for x in r.digests.numpy()] == want_hashes and r.stats == want_stats
-                assert np.array_equal(r.thumbs[5].numpy(), want_thumb)
+                assert [bytes(x).hex() for x in r.digests] == want_hashes and r.stats == want_stats
+                assert np.array_equal(r.thumbs[5], want_thumb)
             with pytest.raises(ics_b200.B2Error):                               # errors stay thread-local
                 labels.label_tally(img[::-1].copy(), cls, act, n_img, k, sorted_by_image=True)
     except BaseException as e:  # noqa: BLE001 - reported by the main thread
