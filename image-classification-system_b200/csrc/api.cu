@@ -1,6 +1,7 @@
 // Library-level entry points of libb2ingest: version, thread-local error text, device check.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace b2 {
@@ -33,6 +34,13 @@ int sm_count() {
 }
 
 }  // namespace b2
+
+// The streaming ingest keeps tens of kernels (one hash launch per ~4 GiB of messages, each alive for as long as its
+// longest message hashes) and several copy / resize streams in flight.  Streams share hardware work queues
+// ("connections", 8 by default, 32 at most) and the GPU overlaps only a few kernels per queue: measured on the
+// config-3 stream, 1 connection = 9.5 GB/s, 8 = 25.6 GB/s, 32 = PCIe bound.  Ask for 32 unless the user chose; the
+// variable is read when the CUDA context is created, so this only helps when the library is loaded before that.
+__attribute__((constructor)) static void b2_on_load() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 
 extern "C" int b2_version(void) { return 2; }
 

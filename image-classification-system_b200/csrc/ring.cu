@@ -13,10 +13,11 @@
 //     [ metadata | images, 16-byte aligned | thumbnails | previews ]
 // allocated first-in first-out; a chunk is released when its hash kernel, its resize kernels and the read-back of
 // its outputs are done, and submit() blocks only when the ring is full (back-pressure).  Per chunk: one H2D burst
-// on the copy stream, ONE hash launch on one of kRingHashStreams streams (warp-pair kernel, lanes ordered by
-// decreasing length), one resize launch per shape present in the chunk (cached tap plans, outputs addressed by
+// on the copy stream, one resize launch per shape present in the chunk (cached tap plans, outputs addressed by
 // position in the chunk), and one contiguous D2H per output kind straight into the listing-order slots of the
-// caller's buffers.  Per listing: the dedupe decision over all its digests on the `fin` stream.
+// caller's buffers.  Per hash GROUP (consecutive chunks, ~4 GiB): ONE hash launch on one of kRingHashStreams
+// streams (warp-pair kernel, lanes ordered by decreasing length over the group).  Per listing: the dedupe decision
+// over all its digests on the `fin` stream.
 #include "common.cuh"
 
 #include <algorithm>
@@ -30,12 +31,13 @@
 
 namespace b2 {
 
-constexpr int kRingHashStreams = 96;         // a chunk's hash runs for the time its LONGEST message needs (up to ~0.8 s for 50 MB)
+constexpr int kRingHashStreams = 32;         // a group's hash runs for the time its LONGEST message needs (up to ~0.8 s for 50 MB)
 constexpr int kRingResizeStreams = 4;
 constexpr uint32_t kRingMaxChunkImages = 4096;
 constexpr uint64_t kRingMinChunkBytes = 32ull << 20;
 
 static inline uint64_t up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+static bool ring_trace() { static const bool t = getenv("B2_RING_TRACE") != nullptr; return t; }   // debug: per-chunk timeline on stderr
 
 struct RingChunk {
     uint64_t off = 0, bytes = 0;             // region of the device ring
@@ -43,6 +45,14 @@ struct RingChunk {
     cudaEvent_t copied = nullptr, hashed = nullptr, resized = nullptr, flushed = nullptr;
     uint8_t *h_meta = nullptr;               // page-locked metadata staging (lives as long as the chunk record)
     size_t h_meta_cap = 0;
+    bool hash_pending = false;               // data chunk of a hash group that has not been launched yet
+};
+
+// A device buffer carved first-in first-out into regions that are released in allocation order.
+struct RingArena {
+    uint8_t *base = nullptr;
+    uint64_t bytes = 0, head = 0;
+    std::deque<RingChunk *> live;            // allocation order
 };
 
 struct RingListing {
@@ -59,6 +69,8 @@ struct RingListing {
     uint32_t launches = 0;
     struct Part { RingChunk *chunk; uint64_t gen; uint32_t hi; };
     std::vector<Part> parts;                 // chunk -> images [.., hi) of the listing, for progress()
+    struct TraceGroup { RingChunk *meta; uint32_t chunks, msgs; uint64_t bytes; };
+    std::vector<TraceGroup> trace_groups;    // trace mode only
 };
 
 }  // namespace b2
@@ -67,18 +79,20 @@ struct b2_ingest_ring {
     int device = 0;
     int out_h = 0, out_w = 0;
     bool want_preview = false;
-    uint64_t ring_bytes = 0, chunk_bytes = 0;
-    uint8_t *d_ring = nullptr;
-    uint64_t head = 0;                       // next allocation offset
-    std::deque<b2::RingChunk *> live;        // allocation order
+    uint64_t ring_bytes = 0, chunk_bytes = 0, hash_group_bytes = 4ull << 30;
+    uint8_t *d_ring = nullptr;               // = data.base: images + outputs; hash offsets are relative to it
+    b2::RingArena data, meta;                // meta: the hash groups' offset / length / order arrays (tail of d_ring)
     std::vector<b2::RingChunk *> spare;
+    std::vector<void *> graveyard;           // outgrown page-locked metadata buffers
     std::vector<b2::RingListing> listings;
     uint64_t next_ticket = 1;
     cudaStream_t copy = nullptr, d2h = nullptr, fin = nullptr;
     cudaStream_t hash[b2::kRingHashStreams] = {};
     cudaStream_t resize[b2::kRingResizeStreams] = {};
     uint32_t next_hash = 0, next_resize = 0;
+    uint32_t n_hash = b2::kRingHashStreams;  // streams in use (B2_RING_HASH_STREAMS: experiments)
     uint64_t stalls = 0;                     // times submit() had to wait for ring space
+    cudaEvent_t t0 = nullptr;                // trace mode: time origin
 };
 
 namespace b2 {
@@ -94,7 +108,7 @@ static void ring_free_chunk(RingChunk *c) {
 }
 
 static cudaError_t ring_new_chunk(b2_ingest_ring *r, RingChunk **out) {
-    if (!r->spare.empty()) {
+    if (!r->spare.empty() && !ring_trace()) {               // trace mode never reuses a record: its events are read at wait()
         *out = r->spare.back();
         r->spare.pop_back();
         return cudaSuccess;
@@ -103,49 +117,69 @@ static cudaError_t ring_new_chunk(b2_ingest_ring *r, RingChunk **out) {
     if (!c) return cudaErrorMemoryAllocation;
     cudaError_t e = cudaSuccess;
     for (cudaEvent_t *ev : {&c->copied, &c->hashed, &c->resized, &c->flushed})
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, ring_trace() ? cudaEventDefault : cudaEventDisableTiming);
     if (e != cudaSuccess) { ring_free_chunk(c); return e; }
     *out = c;
     return cudaSuccess;
 }
 
-// Release the oldest live chunk (waiting for it when `block`).  Returns false when nothing could be released.
-static bool ring_retire_oldest(b2_ingest_ring *r, bool block, cudaError_t *err) {
-    if (r->live.empty()) return false;
-    RingChunk *c = r->live.front();
+// Page-locked metadata staging of a chunk record.  Never freed while the ring lives: cudaFreeHost synchronises the
+// whole device, i.e. waits for every hash kernel in flight (measured: a record that alternated between the 1 KB chunk
+// role and the 6 KB group role was reallocated on every reuse and serialised the stream at one listing per 0.9 s).
+static cudaError_t ring_meta_reserve(b2_ingest_ring *r, RingChunk *c, uint64_t bytes) {
+    if (c->h_meta_cap >= bytes) return cudaSuccess;
+    if (c->h_meta) r->graveyard.push_back(c->h_meta);        // freed by destroy
+    c->h_meta = nullptr;
+    c->h_meta_cap = 0;
+    size_t want = 128 << 10;
+    while (want < bytes) want *= 2;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&c->h_meta), want, cudaHostAllocDefault);
+    if (e == cudaSuccess) c->h_meta_cap = want;
+    return e;
+}
+
+// Release the oldest live region of an arena (waiting for it when `block`).  Returns 1 = released, 0 = nothing could
+// be released now, 2 = the oldest region belongs to a hash group that has not been launched (the caller must close
+// the group first), -1 = CUDA error in *err.
+static int ring_retire_oldest(b2_ingest_ring *r, RingArena &a, bool block, cudaError_t *err) {
+    if (a.live.empty()) return 0;
+    RingChunk *c = a.live.front();
+    if (c->hash_pending) return 2;
     if (!block) {
         if (cudaEventQuery(c->hashed) != cudaSuccess || cudaEventQuery(c->flushed) != cudaSuccess) {
             cudaGetLastError();                              // cudaErrorNotReady is not an error
-            return false;
+            return 0;
         }
     } else {
         cudaError_t e = cudaEventSynchronize(c->hashed);
         if (e == cudaSuccess) e = cudaEventSynchronize(c->flushed);
-        if (e != cudaSuccess) { *err = e; return false; }
+        if (e != cudaSuccess) { *err = e; return -1; }
     }
-    r->live.pop_front();
+    a.live.pop_front();
     ++c->gen;
     r->spare.push_back(c);
-    return true;
+    return 1;
 }
 
-// First-in first-out allocation of `bytes` (a multiple of 256) in the ring; blocks while the ring is full.
-static cudaError_t ring_alloc(b2_ingest_ring *r, uint64_t bytes, uint64_t *off) {
-    cudaError_t err = cudaSuccess;
-    while (ring_retire_oldest(r, false, &err)) {}
+// First-in first-out allocation of `bytes` (a multiple of 256) in an arena; blocks while it is full.
+// Returns 0 = ok, 2 = blocked by the open hash group (close it and retry), -1 = CUDA error in *err.
+static int ring_alloc(b2_ingest_ring *r, RingArena &a, uint64_t bytes, uint64_t *off, cudaError_t *err) {
+    while (ring_retire_oldest(r, a, false, err) == 1) {}
     for (;;) {
-        if (r->live.empty()) { r->head = 0; }
-        uint64_t cand = r->head + bytes <= r->ring_bytes ? r->head : 0;
+        if (a.live.empty()) a.head = 0;
+        uint64_t cand = a.head + bytes <= a.bytes ? a.head : 0;
         bool clash = false;
-        for (const RingChunk *c : r->live)
+        for (const RingChunk *c : a.live)
             if (cand < c->off + c->bytes && c->off < cand + bytes) { clash = true; break; }
         if (!clash) {
             *off = cand;
-            r->head = cand + bytes;
-            return cudaSuccess;
+            a.head = cand + bytes;
+            return 0;
         }
         ++r->stalls;
-        if (!ring_retire_oldest(r, true, &err)) return err != cudaSuccess ? err : cudaErrorUnknown;
+        const int rc = ring_retire_oldest(r, a, true, err);
+        if (rc == 2 || rc == -1) return rc;
+        if (rc == 0) { *err = cudaErrorUnknown; return -1; }
     }
 }
 
@@ -156,9 +190,11 @@ static void ring_drain(b2_ingest_ring *r) {                  // error path: noth
     cudaStreamSynchronize(r->d2h);
     cudaStreamSynchronize(r->fin);
     cudaGetLastError();
-    for (RingChunk *c : r->live) { ++c->gen; r->spare.push_back(c); }
-    r->live.clear();
-    r->head = 0;
+    for (RingArena *a : {&r->data, &r->meta}) {
+        for (RingChunk *c : a->live) { ++c->gen; c->hash_pending = false; r->spare.push_back(c); }
+        a->live.clear();
+        a->head = 0;
+    }
 }
 
 int cached_plan(int device, int ih, int iw, int oh, int ow, b2_resize_plan **out);   // host.cu
@@ -170,6 +206,7 @@ extern "C" int b2_ingest_ring_destroy(b2_ingest_ring *r) {
     cudaSetDevice(r->device);
     if (r->copy) b2::ring_drain(r);
     for (auto *c : r->spare) b2::ring_free_chunk(c);
+    for (void *p : r->graveyard) cudaFreeHost(p);
     for (auto &l : r->listings) {
         cudaFree(l.d_digests); cudaFree(l.d_is_new); cudaFree(l.d_valid); cudaFree(l.d_existing);
         cudaFree(l.d_first); cudaFree(l.d_last); cudaFree(l.d_counts); cudaFree(l.d_ws);
@@ -204,6 +241,10 @@ extern "C" int b2_ingest_ring_create(int device, uint64_t ring_bytes, uint64_t c
     r->chunk_bytes = chunk_bytes ? chunk_bytes : (1ull << 30);
     if (r->chunk_bytes > r->ring_bytes / 4) r->chunk_bytes = r->ring_bytes / 4;
     r->listings.resize(max_listings);
+    if (const char *e = getenv("B2_RING_HASH_GROUP_MB"))
+        if (atoll(e) >= 1) r->hash_group_bytes = uint64_t(atoll(e)) << 20;
+    if (const char *e = getenv("B2_RING_HASH_STREAMS"))
+        r->n_hash = uint32_t(atoi(e)) >= 1 && uint32_t(atoi(e)) <= uint32_t(kRingHashStreams) ? uint32_t(atoi(e)) : r->n_hash;
 #define B2_TRY(expr)                                                                                    \
     do {                                                                                                \
         cudaError_t _e = (expr);                                                                        \
@@ -213,6 +254,10 @@ extern "C" int b2_ingest_ring_create(int device, uint64_t ring_bytes, uint64_t c
         }                                                                                               \
     } while (0)
     B2_TRY(cudaMalloc(&r->d_ring, size_t(r->ring_bytes)));
+    r->meta.bytes = std::min<uint64_t>(64ull << 20, r->ring_bytes / 16) & ~uint64_t(255);     // 20 bytes per message in flight
+    r->data.base = r->d_ring;
+    r->data.bytes = r->ring_bytes - r->meta.bytes;
+    r->meta.base = r->d_ring + r->data.bytes;
     int prio_low = 0, prio_high = 0;
     B2_TRY(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
     B2_TRY(cudaStreamCreateWithPriority(&r->copy, cudaStreamNonBlocking, prio_low));
@@ -221,6 +266,10 @@ extern "C" int b2_ingest_ring_create(int device, uint64_t ring_bytes, uint64_t c
     // the hash kernels are the long pole: their CTAs are placed first
     for (auto &st : r->hash) B2_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_high));
     for (auto &st : r->resize) B2_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_low));
+    if (ring_trace()) {
+        B2_TRY(cudaEventCreate(&r->t0));
+        B2_TRY(cudaEventRecord(r->t0, r->copy));
+    }
     for (auto &l : r->listings) {
         B2_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
         B2_TRY(cudaMalloc(&l.d_counts, 16));
@@ -315,6 +364,7 @@ extern "C" int b2_ingest_ring_submit(b2_ingest_ring *r, const uint8_t *const *h_
     L->h2d = L->d2h = 0;
     L->launches = 0;
     L->parts.clear();
+    L->trace_groups.clear();
     if (m) {
         B2_TRY(cudaMemcpyAsync(L->d_existing, h_existing_sorted, size_t(m) * 32, cudaMemcpyHostToDevice, r->copy));
         L->h2d += m * 32;
@@ -324,10 +374,79 @@ extern "C" int b2_ingest_ring_submit(b2_ingest_ring *r, const uint8_t *const *h_
         L->h2d += n;
     }
 
-    std::vector<uint32_t> order, grouped;
+    // Hash GROUPS: the messages of several consecutive chunks are hashed by ONE launch (lanes ordered by decreasing
+    // length over the whole group), issued when the group's last chunk has been copied.  A hash kernel lives as long
+    // as its longest message (0.8 s for 50 MB) and the GPU runs only a few kernels per hardware connection at once
+    // (measured: 1 connection ~8 concurrent kernels, the default 8 connections ~20), so the bytes one hash launch
+    // carries — not the copy granularity — decide how many bytes can hash at the same time.
+    const uint64_t group_bytes = std::max<uint64_t>(chunk_bytes, std::min<uint64_t>(r->hash_group_bytes, listing_bytes / 2));
+    struct Msg { uint64_t off, len; };
+    std::vector<Msg> gmsgs;                                  // messages of the open hash group
+    std::vector<RingChunk *> gchunks;                        // its data chunks
+    uint32_t g_lo = 0;                                       // listing position of its first message
+    uint64_t g_bytes = 0;
+    std::vector<uint32_t> order;
     std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> groups;
+
+    auto close_hash_group = [&](cudaError_t *ce) -> int {
+        *ce = cudaSuccess;
+        const uint32_t cnt = uint32_t(gmsgs.size());
+        if (!cnt) return B2_OK;
+        // the group's metadata gets its own small region of the ring (released after the hash)
+        const uint64_t o_hlen = 8ull * cnt, o_order = 16ull * cnt, meta_bytes = 20ull * cnt, total = up(meta_bytes, 256);
+        RingChunk *c = nullptr;
+        if ((*ce = ring_new_chunk(r, &c)) != cudaSuccess) return B2_ERR_CUDA;
+        if ((*ce = ring_meta_reserve(r, c, meta_bytes)) != cudaSuccess) {
+            r->spare.push_back(c);
+            return B2_ERR_CUDA;
+        }
+        if (total > r->meta.bytes) { r->spare.push_back(c); return fail(B2_ERR_BAD_ARG, "b2_ingest_ring_submit: hash group of %u messages exceeds the metadata arena", cnt); }
+        uint64_t off = 0;
+        if (ring_alloc(r, r->meta, total, &off, ce) != 0) { r->spare.push_back(c); return B2_ERR_CUDA; }   // never blocked by an open group
+        c->off = off;
+        c->bytes = total;
+        c->hash_pending = false;
+        r->meta.live.push_back(c);
+        uint64_t *m_hoff = reinterpret_cast<uint64_t *>(c->h_meta), *m_hlen = reinterpret_cast<uint64_t *>(c->h_meta + o_hlen);
+        uint32_t *m_order = reinterpret_cast<uint32_t *>(c->h_meta + o_order);
+        for (uint32_t j = 0; j < cnt; ++j) { m_hoff[j] = gmsgs[j].off; m_hlen[j] = gmsgs[j].len; }
+        order.resize(cnt);
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return gmsgs[x].len > gmsgs[y].len; });
+        memcpy(m_order, order.data(), 4ull * cnt);
+        uint8_t *d_meta = r->meta.base + c->off;
+        if ((*ce = cudaMemcpyAsync(d_meta, c->h_meta, size_t(meta_bytes), cudaMemcpyHostToDevice, r->copy)) != cudaSuccess) return B2_ERR_CUDA;
+        L->h2d += meta_bytes;
+        if ((*ce = cudaEventRecord(c->copied, r->copy)) != cudaSuccess) return B2_ERR_CUDA;   // after every data chunk of the group too
+        cudaStream_t hs = r->hash[r->next_hash++ % r->n_hash];
+        if ((*ce = cudaStreamWaitEvent(hs, c->copied, 0)) != cudaSuccess) return B2_ERR_CUDA;
+        int rc = b2_sha256_batch(r->d_ring, reinterpret_cast<const uint64_t *>(d_meta), reinterpret_cast<const uint64_t *>(d_meta + o_hlen),
+                                 reinterpret_cast<const uint32_t *>(d_meta + o_order), cnt, L->d_digests + size_t(g_lo) * 32, hs);
+        if (rc != B2_OK) return rc;
+        ++L->launches;
+        if ((*ce = cudaEventRecord(c->hashed, hs)) != cudaSuccess) return B2_ERR_CUDA;
+        for (RingChunk *dc : gchunks) {                      // the data chunks are released by the same moment
+            if ((*ce = cudaEventRecord(dc->hashed, hs)) != cudaSuccess) return B2_ERR_CUDA;
+            dc->hash_pending = false;
+        }
+        if ((*ce = cudaEventRecord(c->flushed, hs)) != cudaSuccess) return B2_ERR_CUDA;
+        if ((*ce = cudaStreamWaitEvent(r->fin, c->hashed, 0)) != cudaSuccess) return B2_ERR_CUDA;
+        if (ring_trace()) L->trace_groups.push_back({c, uint32_t(gchunks.size()), cnt, g_bytes});
+        gmsgs.clear();
+        gchunks.clear();
+        g_bytes = 0;
+        return B2_OK;
+    };
+#define B2_CLOSE_GROUP()                                                                                \
+    do {                                                                                                \
+        cudaError_t _ce = cudaSuccess;                                                                  \
+        int _rc = close_hash_group(&_ce);                                                               \
+        if (_ce != cudaSuccess) { B2_TRY(_ce); }                                                        \
+        if (_rc != B2_OK) { ring_drain(r); return _rc; }                                                \
+    } while (0)
+
     for (uint32_t lo = 0; lo < n;) {
-        // ---- chunk = consecutive listing entries up to chunk_bytes
+        // ---- chunk = consecutive listing entries up to chunk_bytes: the unit of copy, resize and read-back
         uint32_t cnt = 0;
         uint64_t data_bytes = 0;
         while (lo + cnt < n && cnt < kRingMaxChunkImages) {
@@ -337,42 +456,45 @@ extern "C" int b2_ingest_ring_submit(b2_ingest_ring *r, const uint8_t *const *h_
             ++cnt;
         }
         // layout inside the chunk region (offsets relative to its start)
-        const uint64_t o_hoff = 0, o_hlen = o_hoff + 8ull * cnt, o_poff = o_hlen + 8ull * cnt,
-                       o_order = o_poff + 8ull * cnt, o_slot = o_order + 4ull * cnt, meta_bytes = o_slot + 4ull * cnt;
+        const uint64_t o_poff = 0, o_slot = 8ull * cnt, meta_bytes = 12ull * cnt;
         const uint64_t o_data = up(meta_bytes, 256);
         const uint64_t o_thumb = up(o_data + data_bytes + 16, 256);
         const uint64_t thumb_bytes = h_pixels ? uint64_t(cnt) * out_px : 0;
         const uint64_t o_prev = up(o_thumb + thumb_bytes, 256);
         const uint64_t prev_bytes = h_pixels && h_previews ? uint64_t(cnt) * out_px * 4 : 0;
         const uint64_t total = up(o_prev + prev_bytes, 256);
-        if (total > r->ring_bytes) {
+        if (total > r->data.bytes) {
             ring_drain(r);
             return fail(B2_ERR_BAD_ARG, "b2_ingest_ring_submit: image %u needs %llu bytes of staging, the ring has %llu",
-                        lo, (unsigned long long)total, (unsigned long long)r->ring_bytes);
+                        lo, (unsigned long long)total, (unsigned long long)r->data.bytes);
+        }
+        if (g_bytes && g_bytes + data_bytes > group_bytes) B2_CLOSE_GROUP();
+        uint64_t region = 0;
+        for (;;) {
+            cudaError_t e = cudaSuccess;
+            const int st = ring_alloc(r, r->data, total, &region, &e);
+            if (st == 2) {                                   // the ring is full of the OPEN group's chunks: hash what is there
+                B2_CLOSE_GROUP();
+                continue;
+            }
+            if (st != 0) B2_TRY(e != cudaSuccess ? e : cudaErrorUnknown);
+            break;
         }
         RingChunk *c = nullptr;
         B2_TRY(ring_new_chunk(r, &c));
-        if (c->h_meta_cap < meta_bytes) {
-            if (c->h_meta) cudaFreeHost(c->h_meta);
-            c->h_meta = nullptr;
-            c->h_meta_cap = 0;
-            const size_t want = size_t(up(meta_bytes, 4096));
-            cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&c->h_meta), want, cudaHostAllocDefault);
-            if (e != cudaSuccess) { r->spare.push_back(c); B2_TRY(e); }
-            c->h_meta_cap = want;
-        }
         {
-            uint64_t off = 0;
-            cudaError_t e = ring_alloc(r, total, &off);
+            cudaError_t e = ring_meta_reserve(r, c, meta_bytes);
             if (e != cudaSuccess) { r->spare.push_back(c); B2_TRY(e); }
-            c->off = off;
-            c->bytes = total;
         }
-        r->live.push_back(c);
+        c->off = region;
+        c->bytes = total;
+        if (gmsgs.empty()) g_lo = lo;
+        c->hash_pending = true;
+        r->data.live.push_back(c);
+        gchunks.push_back(c);
         uint8_t *d_chunk = r->d_ring + c->off;
-        uint64_t *m_hoff = reinterpret_cast<uint64_t *>(c->h_meta + o_hoff), *m_hlen = reinterpret_cast<uint64_t *>(c->h_meta + o_hlen),
-                 *m_poff = reinterpret_cast<uint64_t *>(c->h_meta + o_poff);
-        uint32_t *m_order = reinterpret_cast<uint32_t *>(c->h_meta + o_order), *m_slot = reinterpret_cast<uint32_t *>(c->h_meta + o_slot);
+        uint64_t *m_poff = reinterpret_cast<uint64_t *>(c->h_meta + o_poff);
+        uint32_t *m_slot = reinterpret_cast<uint32_t *>(c->h_meta + o_slot);
 
         // ---- placement + copies (adjacent host buffers that land adjacently on the device travel as one copy)
         groups.clear();
@@ -404,36 +526,23 @@ extern "C" int b2_ingest_ring_submit(b2_ingest_ring *r, const uint8_t *const *h_
                 groups[{h_hw[2 * i], h_hw[2 * i + 1]}].push_back(j);
             }
             if (h_files) {
-                m_hoff[j] = pos;
-                m_hlen[j] = ml;
+                gmsgs.push_back({pos, ml});
                 if (ml) B2_TRY(put(h_files[i], ml));
                 pos += up(ml, 16);
             } else {
-                m_hoff[j] = pl ? pix_off[j] : pos;
-                m_hlen[j] = ml;
+                gmsgs.push_back({pl ? pix_off[j] : pos, ml});
             }
         }
         B2_TRY(flush_run());
-        order.resize(cnt);
-        std::iota(order.begin(), order.end(), 0u);
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return m_hlen[a] > m_hlen[b]; });
-        memcpy(m_order, order.data(), 4ull * cnt);
+        g_bytes += data_bytes;
         uint32_t g = 0;
         for (auto &kv : groups)
             for (uint32_t j : kv.second) { m_poff[g] = pix_off[j]; m_slot[g] = j; ++g; }
-        B2_TRY(cudaMemcpyAsync(d_chunk, c->h_meta, size_t(meta_bytes), cudaMemcpyHostToDevice, r->copy));
-        L->h2d += meta_bytes;
+        if (g) {
+            B2_TRY(cudaMemcpyAsync(d_chunk, c->h_meta, size_t(meta_bytes), cudaMemcpyHostToDevice, r->copy));
+            L->h2d += meta_bytes;
+        }
         B2_TRY(cudaEventRecord(c->copied, r->copy));
-
-        // ---- hash: one launch for the chunk, digests straight into the listing's slots
-        cudaStream_t hs = r->hash[r->next_hash++ % kRingHashStreams];
-        B2_TRY(cudaStreamWaitEvent(hs, c->copied, 0));
-        B2_TRY_RC(b2_sha256_batch(r->d_ring, reinterpret_cast<const uint64_t *>(d_chunk + o_hoff),
-                                  reinterpret_cast<const uint64_t *>(d_chunk + o_hlen),
-                                  reinterpret_cast<const uint32_t *>(d_chunk + o_order), cnt, L->d_digests + size_t(lo) * 32, hs));
-        B2_TRY(cudaEventRecord(c->hashed, hs));
-        B2_TRY(cudaStreamWaitEvent(r->fin, c->hashed, 0));
-        ++L->launches;
 
         // ---- resize: one launch per shape in the chunk, then one read-back per output kind
         if (g) {
@@ -471,6 +580,9 @@ extern "C" int b2_ingest_ring_submit(b2_ingest_ring *r, const uint8_t *const *h_
         lo += cnt;
         L->parts.push_back({c, c->gen, lo});
     }
+    RingChunk *last_data = L->parts.back().chunk;
+    B2_CLOSE_GROUP();
+#undef B2_CLOSE_GROUP
 
     // ---- the listing's dedupe decision, after every chunk's hash (fin already waits for them)
     B2_TRY(cudaEventRecord(L->done, r->copy));               // existing table / validity flags copied
@@ -490,7 +602,7 @@ extern "C" int b2_ingest_ring_submit(b2_ingest_ring *r, const uint8_t *const *h_
         B2_TRY(cudaMemcpyAsync(h_last_index, L->d_last, size_t(n) * 4, cudaMemcpyDeviceToHost, r->fin));
         L->d2h += uint64_t(n) * 4;
     }
-    B2_TRY(cudaStreamWaitEvent(r->fin, L->parts.back().chunk->flushed, 0));   // the d2h stream is in order: last chunk = all chunks
+    B2_TRY(cudaStreamWaitEvent(r->fin, last_data->flushed, 0));   // the d2h stream is in order: last chunk = all chunks
     B2_TRY(cudaEventRecord(L->done, r->fin));
 #undef B2_TRY
 #undef B2_TRY_RC
@@ -515,6 +627,16 @@ extern "C" int b2_ingest_ring_wait(b2_ingest_ring *r, uint64_t ticket, uint64_t 
     B2_REQUIRE(L != nullptr, "b2_ingest_ring_wait: ticket %llu is not in flight", (unsigned long long)ticket);
     B2_CUDA_CHECK(cudaSetDevice(r->device));
     cudaError_t e = cudaEventSynchronize(L->done);
+    if (ring_trace() && e == cudaSuccess) {
+        auto ms = [&](cudaEvent_t ev) { float t = -1.f; if (cudaEventElapsedTime(&t, r->t0, ev) != cudaSuccess) { cudaGetLastError(); t = -1.f; } return t; };
+        for (const auto &p : L->parts)
+            fprintf(stderr, "[ring] L%llu chunk hi=%u bytes=%llu copied=%.1f resized=%.1f flushed=%.1f hashed=%.1f\n", (unsigned long long)ticket,
+                    p.hi, (unsigned long long)p.chunk->bytes, ms(p.chunk->copied), ms(p.chunk->resized), ms(p.chunk->flushed), ms(p.chunk->hashed));
+        for (const auto &g : L->trace_groups)
+            fprintf(stderr, "[ring] L%llu group chunks=%u msgs=%u bytes=%llu copied=%.1f hashed=%.1f\n", (unsigned long long)ticket, g.chunks, g.msgs,
+                    (unsigned long long)g.bytes, ms(g.meta->copied), ms(g.meta->hashed));
+    }
+    L->trace_groups.clear();
     L->pending = false;
     L->parts.clear();
     if (e != cudaSuccess) return fail(B2_ERR_CUDA, "b2_ingest_ring_wait: %s", cudaGetErrorString(e));
@@ -551,10 +673,11 @@ extern "C" int b2_ingest_ring_stats(const b2_ingest_ring *r, uint64_t *ring_byte
     using namespace b2;
     B2_REQUIRE(r != nullptr, "b2_ingest_ring_stats: null ring");
     uint64_t b = 0;
-    for (const RingChunk *c : r->live) b += c->bytes;
+    for (const RingChunk *c : r->data.live) b += c->bytes;
+    for (const RingChunk *c : r->meta.live) b += c->bytes;
     if (ring_bytes) *ring_bytes = r->ring_bytes;
     if (bytes_in_flight) *bytes_in_flight = b;
-    if (chunks_in_flight) *chunks_in_flight = uint32_t(r->live.size());
+    if (chunks_in_flight) *chunks_in_flight = uint32_t(r->data.live.size());
     if (stalls) *stalls = r->stalls;
     return B2_OK;
 }

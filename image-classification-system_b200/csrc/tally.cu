@@ -193,9 +193,9 @@ constexpr int kSlabStageBytes = kSlabStageRows * 6;               // 25 344
 constexpr int kSlabThreads = 256;
 constexpr int kSlabWarps = kSlabThreads / 32;
 
-__host__ __device__ inline size_t slab_smem_bytes(uint32_t stages, uint32_t tile_images, uint32_t k) {
+__host__ __device__ inline size_t slab_smem_bytes(uint32_t stages, uint32_t tile_images, uint32_t k, bool hist) {
     return size_t(stages) * kSlabStageBytes + ((size_t(tile_images) * k * 4 + 15) & ~size_t(15)) + 1024 +
-           size_t(k) * 8 + 8 * 8 + 16 + size_t(stages) * 8 + size_t(kAgreeBins) * 8;
+           size_t(k) * 8 + 8 * 8 + 16 + size_t(stages) * 8 + (hist ? size_t(kAgreeBins) * 4 : 0);
 }
 
 // One row of a quad, branch-free: in the window and class in range => seen++; also active => one shared
@@ -254,8 +254,28 @@ __device__ __forceinline__ void slab_row(int32_t img, uint32_t cw, uint32_t aw, 
           "r"(k4), "r"(tile_s), "r"(one));
 }
 
-// KC = classes per lane (k <= 32 KC), NS = ring depth, kInc = warp-aggregated increments (long images)
-template <int KC, int NS, bool kInc>
+// The slab kernel's form: 32-bit counters in shared memory, ONE fire-and-forget shared atomic per lane for the 32
+// images parked in a warp's lanes (a warp-aggregated 64-bit form cost +24 % warp instructions, ncu r2).  A numerator
+// is < 2^20 (n < kAgreeBins = 2^10), so a bin cannot overflow before kHistFlushImages images have been folded; the CTA
+// commits its bins to global memory (64-bit atomics) and zeroes them before that.
+constexpr uint32_t kHistFlushImages = 3968;                  // + one window of <= 128 images stays below 2^12
+__device__ __forceinline__ void agree_add_lane(uint32_t *s_hist32, uint32_t n, uint32_t s2) {
+    const bool big = n >= kAgreeBins;
+    if (n >= 2u) atomicAdd(&s_hist32[big ? 0u : n], big ? 1u : s2 - n);
+}
+__device__ __forceinline__ void commit_hist32(uint32_t *s_hist32, unsigned long long *g_hist) {
+    for (uint32_t i = threadIdx.x; i < kAgreeBins; i += blockDim.x) {
+        const uint32_t v = s_hist32[i];
+        if (v) {
+            atomicAdd(&g_hist[i], (unsigned long long)v);
+            s_hist32[i] = 0u;
+        }
+    }
+}
+
+// KC = classes per lane (k <= 32 KC), NS = ring depth, kInc = warp-aggregated increments (long images),
+// kHist = also build the agreement histogram (g_hist != NULL)
+template <int KC, int NS, bool kInc, bool kHist>
 __global__ void __launch_bounds__(kSlabThreads, 2)
 tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
                   const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
@@ -270,7 +290,7 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
     unsigned long long *part = class_tot + k;                    // 8 (7 used)
     int32_t *s_beyond = reinterpret_cast<int32_t *>(part + 8);   // 1 (+ padding to 16 bytes)
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_beyond + 4);
-    unsigned long long *hist = reinterpret_cast<unsigned long long *>(bars + NS);   // kAgreeBins (used when g_hist != NULL)
+    uint32_t *hist = reinterpret_cast<uint32_t *>(bars + NS);   // kAgreeBins 32-bit bins (kHist only)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
 
     const uint32_t G = gridDim.x, b = blockIdx.x;
@@ -296,7 +316,7 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
 
     for (uint32_t e = tid; e < T * k; e += kSlabThreads) tile[e] = 0;
     for (uint32_t c = tid; c < k + 8; c += kSlabThreads) class_tot[c] = 0;      // class totals + partials
-    if (g_hist)
+    if (kHist)
         for (uint32_t c = tid; c < kAgreeBins; c += kSlabThreads) hist[c] = 0;
     if (tid == 0) {
 #pragma unroll
@@ -307,14 +327,14 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
 
     // Per-lane accumulators of the flushes; reduced across the CTA once, at the end of the kernel.
     unsigned long long tot[KC], s2 = 0, pairs = 0;                // tot[cc]: class lane + 32 cc
-    uint32_t rated = 0, pair_images = 0;
+    uint32_t rated = 0, pair_images = 0, hist_images = 0;
 #pragma unroll
     for (int cc = 0; cc < KC; ++cc) tot[cc] = 0;
     auto fold_image = [&](uint32_t n, uint32_t s2i) {             // n_i and sum_j n_ij^2 of one image (0 is harmless)
         rated += n >= 1u;
         pair_images += n >= 2u;
         pairs += (unsigned long long)n * (n - 1u);                // 0 * 0xffffffff = 0
-        if (g_hist) agree_add(hist, n, s2i);                      // s2i may have wrapped for n >= 65536: unused from kAgreeBins up
+        if (kHist) agree_add_lane(hist, n, s2i);                  // s2i may have wrapped for n >= 65536: unused from kAgreeBins up
     };
 
     // Write images [a, e) (complete, all mine) to d_counts, fold them into the partials, leave their
@@ -345,11 +365,11 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
                 }
                 tot[cc] += v[cc];
                 s2 += (unsigned long long)v[cc] * v[cc];
-                s2i += v[cc] * v[cc];
+                if (kHist) s2i += v[cc] * v[cc];
                 n += v[cc];
             }
             n = __reduce_add_sync(0xffffffffu, n);
-            if (g_hist) s2i = __reduce_add_sync(0xffffffffu, s2i);
+            if (kHist) s2i = __reduce_add_sync(0xffffffffu, s2i);
             if ((it & 31u) == lane) { n_mine = n; s2_mine = s2i; }
             if ((it & 31u) == 31u) { fold_image(n_mine, s2_mine); n_mine = 0; s2_mine = 0; }
         }
@@ -360,6 +380,14 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
             for (size_t i = tid; i < ne; i += kSlabThreads) z[i] = 0;
         }
         __syncthreads();
+        if (kHist) {
+            hist_images += n_ring;
+            if (hist_images >= kHistFlushImages) {                // uniform: before a 32-bit bin can overflow
+                commit_hist32(hist, g_hist);
+                hist_images = 0;
+                __syncthreads();
+            }
+        }
     };
 
     uint32_t seen = 0, unsorted = 0;
@@ -536,7 +564,7 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
     part_add(part, P_UNSORTED, unsorted);
     __syncthreads();
     commit_partials(part, class_tot, k, g_partials);
-    if (g_hist) commit_hist(hist, g_hist);
+    if (kHist) commit_hist32(hist, g_hist);
 }
 
 // Any row order: one RED.ADD per active row into a zeroed count matrix.
@@ -674,9 +702,9 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
         if (const char *e = getenv("B2_TALLY_CTAS")) per_sm = uint32_t(atoi(e)) < 1 ? 1u : uint32_t(atoi(e));
         const size_t budget = (227u * 1024u) / per_sm - 1024u;               // per CTA, incl. the 1 KB the driver reserves
         uint32_t t = 0;
-        while (t < 13 && slab_smem_bytes(stages, 2u << t, k) <= budget) ++t;
+        while (t < 13 && slab_smem_bytes(stages, 2u << t, k, hist != nullptr) <= budget) ++t;
         if (const char *e = getenv("B2_TALLY_TILE_LOG2")) t = uint32_t(atoi(e));
-        const size_t smem_slab = slab_smem_bytes(stages, 1u << t, k);
+        const size_t smem_slab = slab_smem_bytes(stages, 1u << t, k, hist != nullptr);
         uint64_t want = rows ? (rows + 2ull * kSlabStageRows - 1) / (2ull * kSlabStageRows)
                              : (uint64_t(n_images) + 1023) / 1024;
         const uint64_t cap_ctas = uint64_t(per_sm) * uint64_t(sm_count());
@@ -684,6 +712,12 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
         if (want < 1) want = 1;
         auto launch = [&](auto kern) -> int {
             B2_CUDA_CHECK(ensure_smem(reinterpret_cast<const void *>(kern), smem_slab));
+            if (getenv("B2_TALLY_DEBUG")) {
+                int occ = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSlabThreads, smem_slab);
+                fprintf(stderr, "[b2] tally_slab_kernel: %u CTAs, %zu B smem, T=2^%u, hist=%d, occupancy %d CTAs/SM\n",
+                        uint32_t(want), smem_slab, t, hist != nullptr, occ);
+            }
             kern<<<uint32_t(want), kSlabThreads, smem_slab, st>>>(d_image_idx, d_class_idx, d_active, rows,
                                                                  int32_t(image_base), n_images, k, t, d_counts, partials, hist);
             B2_LAUNCH_CHECK("tally_slab_kernel");
@@ -694,12 +728,17 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
         // per image 0.125 ms plain / 0.129 aggregated; 1 000: 0.145 / 0.116; 10 000: 0.278 / 0.114.
         bool inc = rows / n_images >= 512;
         if (const char *e = getenv("B2_TALLY_INC")) inc = atoi(e) != 0;
+#define B2_SLAB_DISPATCH_H(NS, INC, HIST)                                             \
+    do {                                                                              \
+        if (k <= 32) return launch(tally_slab_kernel<1, NS, INC, HIST>);              \
+        if (k <= 64) return launch(tally_slab_kernel<2, NS, INC, HIST>);              \
+        if (k <= 128) return launch(tally_slab_kernel<4, NS, INC, HIST>);             \
+        return launch(tally_slab_kernel<8, NS, INC, HIST>);                           \
+    } while (0)
 #define B2_SLAB_DISPATCH(NS, INC)                                                     \
     do {                                                                              \
-        if (k <= 32) return launch(tally_slab_kernel<1, NS, INC>);                    \
-        if (k <= 64) return launch(tally_slab_kernel<2, NS, INC>);                    \
-        if (k <= 128) return launch(tally_slab_kernel<4, NS, INC>);                   \
-        return launch(tally_slab_kernel<8, NS, INC>);                                 \
+        if (hist) B2_SLAB_DISPATCH_H(NS, INC, true);                                  \
+        B2_SLAB_DISPATCH_H(NS, INC, false);                                           \
     } while (0)
         if (stages == 2) {
             if (inc) B2_SLAB_DISPATCH(2, true);
@@ -708,6 +747,7 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
         if (inc) B2_SLAB_DISPATCH(3, true);
         B2_SLAB_DISPATCH(3, false);
 #undef B2_SLAB_DISPATCH
+#undef B2_SLAB_DISPATCH_H
     }
     B2_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, size_t(n_images) * k * 4, st));
     if (rows) {

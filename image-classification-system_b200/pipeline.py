@@ -91,6 +91,21 @@ class IngestRing:
         self._free: List[_Slot] = []
         self._inflight: Dict[int, _Slot] = {}
 
+    def prepare(self, n_images: Optional[int] = None, n_slots: Optional[int] = None) -> None:
+        """Allocate the page-locked result buffers up front (``n_slots`` listings of up to ``n_images`` entries each;
+        defaults: ``max_images`` / ``max_listings``).  Page-locking ~1 MB per image costs ~0.25 s per GB, which would
+        otherwise be paid by the first ``submit`` that needs a new slot.  Frees idle slots of another size."""
+        assert not self._inflight, "prepare() with listings in flight"
+        n_images = n_images or self.max_images
+        n_slots = min(n_slots or self.max_listings, self.max_listings)
+        keep = [s for s in self._free if s.cap == n_images][:n_slots]
+        self._slots = self._free = None                      # drop the others before allocating
+        self._slots, self._free = list(keep), list(keep)
+        while len(self._slots) < n_slots:
+            s = _Slot(n_images, self.out_h, self.out_w, self.want_preview)
+            self._slots.append(s)
+            self._free.append(s)
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             lib.b2_ingest_ring_destroy(self._h)

@@ -40,7 +40,7 @@ def test_pipeline_matches_oracle(shape, n, chunk):
             np.testing.assert_allclose(res.previews[i], preview_f32(want), rtol=1e-5, atol=1e-7)
         n_chunks = -(-n // chunk)
         assert n * shape[0] * shape[1] * 3 <= res.h2d_bytes <= n * (shape[0] * shape[1] * 3 + 32)   # images + chunk metadata
-        assert res.kernel_launches == 2 * n_chunks + 2    # per chunk: one hash, one resize; per listing: dedupe insert + resolve
+        assert n_chunks + 1 + 2 <= res.kernel_launches <= 2 * n_chunks + 2   # resize per chunk, hash per group of chunks, dedupe insert + resolve
     pipe.close()
 
 
@@ -97,7 +97,7 @@ def test_native_ring_from_plain_ctypes_and_numpy():
     assert lib.b2_ingest_ring_wait(ring, u64(999), None, None, None) == -1            # unknown ticket
     assert lib.b2_ingest_ring_wait(ring, ticket, C.byref(h2d), C.byref(d2h), C.byref(launches)) == 0
     assert lib.b2_ingest_ring_wait(ring, ticket, None, None, None) == -1              # already waited for
-    assert h2d.value >= n * L and launches.value == 2 * 3 + 2
+    assert h2d.value >= n * L and 3 + 1 + 2 <= launches.value <= 2 * 3 + 2
     assert [bytes(d).hex() for d in h_dig.reshape(n, 32)] == [sha256_hex(im.tobytes()) for im in images]
     assert h_new.tolist() == [1] * n and h_cnt[:3].tolist() == [n, n, 0]
     assert np.array_equal(h_th.reshape(n, 256, 256, 3)[5], thumbnail_u8(images[5], 256, 256))

@@ -75,10 +75,13 @@ def main():
         act = (torch.rand(rows, device=dev, generator=g) < 0.95).to(torch.uint8)
         counts = torch.empty((N, k), dtype=torch.int32, device=dev)
         part = torch.empty(k + 7, dtype=torch.int64, device=dev)
-        ms = timed(lambda: engine.label_tally_device(img, cls, act, N, k, 0, True, counts, part),
-                   reps=int(os.environ.get("B2_PROF_REPS", "20")))
+        reps = int(os.environ.get("B2_PROF_REPS", "20"))
+        ms = timed(lambda: engine.label_tally_device(img, cls, act, N, k, 0, True, counts, part), reps=reps)
         b = 6 * rows + 4 * N * k
         print(f"tally: {rows} rows  {ms:.3f} ms  {b / ms / 1e6:.1f} GB/s")
+        hist = torch.empty(1024, dtype=torch.int64, device=dev)
+        ms = timed(lambda: engine.label_tally_device(img, cls, act, N, k, 0, True, counts, part, hist), reps=reps)
+        print(f"tally + agreement histogram: {rows} rows  {ms:.3f} ms  {b / ms / 1e6:.1f} GB/s")
 
 
 if __name__ == "__main__":
