@@ -84,10 +84,82 @@ def sha256_host(datas: Sequence[bytes], device: Optional[int] = None, want_hex: 
     return digests, [flat[i:i + 64] for i in range(0, n * 64, 64)]
 
 
+class _HashCoalescer:
+    """Merges CONCURRENT small ``hash_batch`` calls into one device launch.
+
+    The reference hashes one file per call from up to five service threads at once (initial sync + its WebDAV and
+    Activity workers, the scheduler's two loops: app/main.py:188-226) plus request threads.  One message costs the GPU
+    as long as 32 of them, so calls that arrive while a launch is in flight are queued and the next launch takes them
+    all: the first caller in becomes the leader, runs ONE ``b2_sha256_host`` over everything queued and hands the
+    results out; followers wait (and take over leadership if the leader has left).  No artificial delay: a lone caller
+    pays nothing, the batching comes from the launch latency itself."""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.queue: list = []                      # entries: [datas, result, error, done-event]
+        self.leader_active = False
+        self.calls = 0                             # hash_batch calls served
+        self.launches = 0                          # device launches issued for them
+
+    def _round(self, device) -> None:
+        with self.lock:
+            batch, self.queue = self.queue, []
+        if not batch:
+            return
+        try:
+            flat = [d for e in batch for d in e[0]]
+            hexes = sha256_host(flat, device)[1]
+            self.launches += 1
+            o = 0
+            for e in batch:
+                e[1] = hexes[o:o + len(e[0])]
+                o += len(e[0])
+        except BaseException as err:  # noqa: BLE001 - every waiter of this round gets the error
+            for e in batch:
+                e[2] = err
+        for e in batch:
+            e[3].set()
+
+    def hash(self, datas: Sequence[bytes], device) -> List[str]:
+        entry = [list(datas), None, None, threading.Event()]
+        with self.lock:
+            self.queue.append(entry)
+            self.calls += 1
+        while not entry[3].is_set():
+            with self.lock:
+                lead = not self.leader_active
+                if lead:
+                    self.leader_active = True
+            if lead:
+                try:
+                    self._round(device)
+                finally:
+                    with self.lock:
+                        self.leader_active = False
+            else:
+                entry[3].wait(0.002)               # woken by the leader; re-checks leadership if it has left
+        if entry[2] is not None:
+            raise entry[2]
+        return entry[1]
+
+
+_coalescers: dict = {}
+_coalescers_lock = threading.Lock()
+COALESCE_MAX_MESSAGES = 64                         # larger batches fill a launch on their own
+
+
 def hash_batch(datas: Sequence[bytes], device: Optional[int] = None) -> List[str]:
     """Batched form of ``hashlib.sha256(data).hexdigest()`` (reference: webdav_sync.py:59,
-    activity_api_sync.py:798, routes/images.py:62) for a list of host byte strings."""
-    return sha256_host(datas, device)[1]
+    activity_api_sync.py:798, routes/images.py:62) for a list of host byte strings.  Small batches from concurrent
+    threads share device launches (:class:`_HashCoalescer`)."""
+    if len(datas) == 0 or len(datas) > COALESCE_MAX_MESSAGES:
+        return sha256_host(datas, device)[1]
+    dev = init(device)
+    with _coalescers_lock:
+        c = _coalescers.get(dev)
+        if c is None:
+            c = _coalescers[dev] = _HashCoalescer()
+    return c.hash(datas, dev)
 
 
 def dedupe_host(digests: np.ndarray, valid: Optional[np.ndarray] = None, existing_sorted: Optional[np.ndarray] = None,

@@ -10,6 +10,7 @@ from datetime import datetime
 from typing import Callable, Dict, Optional
 
 from .. import hostapi
+from ..store import DuplicateKeyError
 from .webdav_sync import WebDAVSync, _utc_now
 
 logger = logging.getLogger(__name__)
@@ -48,9 +49,11 @@ class ActivityAPISync:
             if not conjunto:
                 return False
 
+            minimal = {"nome_img": image_info.get("name", ""), "caminho_img": image_info.get("path", ""),
+                       "existe_no_nextcloud": True, "data_sinc": now}
             if row is None:
                 lm = image_info.get("last_modified")
-                self.db.insert({
+                new_row = {
                     "content_hash": content_hash,
                     "nome_img": image_info.get("name", ""),
                     "caminho_img": image_info.get("path", ""),
@@ -69,14 +72,20 @@ class ActivityAPISync:
                     "data_proc": now,
                     "data_sinc": now,
                     "id_cnj": conjunto["id_cnj"],
-                })
-            else:
-                self.db.update(content_hash, {
-                    "nome_img": image_info.get("name", ""),
-                    "caminho_img": image_info.get("path", ""),
-                    "existe_no_nextcloud": True,
-                    "data_sinc": now,
-                })
+                }
+                try:
+                    self.db.insert(new_row)
+                    self.db.commit()
+                    return True
+                except DuplicateKeyError:
+                    # another session inserted the same content first: merge into its row (:875-887)
+                    self.db.rollback()
+                    if self.db.get(content_hash) is None:
+                        return False
+                    self.db.update(content_hash, minimal)
+                    self.db.commit()
+                    return True
+            self.db.update(content_hash, minimal)
             self.db.commit()
             return True
         except Exception as e:  # noqa: BLE001 - same contract as the reference: log, rollback, False

@@ -30,6 +30,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 from .. import hostapi
 from ..feeder import DownloadDecodeFeeder, FeederBatch, image_metadata
 from ..ingest import hash_and_dedupe
+from ..store import DuplicateKeyError
 
 logger = logging.getLogger(__name__)
 
@@ -51,7 +52,7 @@ class WebDAVSync:
 
     def __init__(self, nextcloud_client, db, now: Callable[[], datetime] = _utc_now,
                  batch_size: int = NEXTCLOUD_SYNC_BATCH_SIZE, device: Optional[int] = None,
-                 download_workers: int = 1, prefetch_batches: int = 1):
+                 download_workers: int = 1, prefetch_batches: int = 1, store_thumbnails: bool = False):
         """``download_workers`` > 1: ``sync_images_in_folder`` downloads through the feeder (``feeder.py``) —
         that many GETs in flight and the next ``prefetch_batches`` batches downloading while the current one is
         hashed and written; 1 = one GET at a time, as the reference does.  Same results either way."""
@@ -62,6 +63,8 @@ class WebDAVSync:
         self.device = device
         self.download_workers = download_workers
         self.prefetch_batches = prefetch_batches
+        # thumbnails of newly inserted images written back through the store (needs the feeder's decoded pixels)
+        self.store_thumbnails = store_thumbnails
 
     # ------------------------------------------------------------------ single-item API
     def _calculate_hash_from_bytes(self, data: bytes) -> str:
@@ -126,45 +129,87 @@ class WebDAVSync:
             logger.error("device ingest failed for batch in %s: %s", folder_path, e)
             return {"processed": 0, "created": 0, "updated": 0}
 
+        # Apply in arrival order.  The device decided created / updated for a table nobody else writes; a concurrent
+        # session (the Activity-API sync runs beside this one) can still insert the same hash first or
+        # remove a row, so every image keeps the reference's own safety net: duplicate key on insert -> rollback,
+        # re-read, minimal merge, counted as updated (:355-369); any other error -> log, rollback, next image
+        # (:421-424).  The stats are therefore counted here; without interference they equal ``decision.stats``.
+        stats = {"processed": 0, "created": 0, "updated": 0}
+        thumbs = self._thumbnails(prefetched, decision) if self.store_thumbnails else None
         for i, info in enumerate(images):
             content_hash = decision.hashes[i]
             if not content_hash:
                 continue
-            if decision.is_new[i]:
-                nc = self._nextcloud_meta(info, full=True)
-                self.db.insert({
-                    "content_hash": content_hash,
-                    "nome_img": info.get("name", ""),
-                    "caminho_img": info.get("path", ""),
-                    "metadados": {
-                        "nextcloud": {"file_id": nc["file_id"], "etag": nc["etag"],
-                                      "content_type": nc["content_type"], "size": nc["size"],
-                                      "last_modified": nc["last_modified"]},
-                        "image": prefetched.metadata[i] if prefetched is not None else self._get_image_metadata(datas[i]),
-                        "sync": {"sync_method": self.SYNC_METHOD, "sync_timestamp": now.isoformat()},
-                    },
-                    "existe_no_nextcloud": True,
-                    "data_proc": now,
-                    "data_sinc": now,
-                    "id_cnj": conjunto_id,
-                })
-            else:
-                row = self.db.get(content_hash)
-                md = row.get("metadados")
-                if md:
-                    if "nextcloud" in md:
-                        md["nextcloud"].update(self._nextcloud_meta(info, full=False))
-                    else:
-                        md["nextcloud"] = self._nextcloud_meta(info, full=True)
-                    md["sync"] = {"sync_method": self.SYNC_METHOD, "sync_timestamp": now.isoformat()}
-                self.db.update(content_hash, {
-                    "nome_img": info.get("name", ""),
-                    "caminho_img": info.get("path", ""),
-                    "existe_no_nextcloud": True,
-                    "data_sinc": now,
-                    "metadados": md,
-                })
-        return dict(decision.stats)
+            try:
+                row = None if decision.is_new[i] else self.db.get(content_hash)
+                if row is None:                               # the insert branch (also: the row vanished meanwhile)
+                    nc = self._nextcloud_meta(info, full=True)
+                    image_md = prefetched.metadata[i] if prefetched is not None else self._get_image_metadata(datas[i])
+                    if thumbs is not None and thumbs[i] is not None:
+                        image_md = dict(image_md, thumb=self.db.put_thumbnail(content_hash, thumbs[i]))
+                    try:
+                        self.db.insert({
+                            "content_hash": content_hash,
+                            "nome_img": info.get("name", ""),
+                            "caminho_img": info.get("path", ""),
+                            "metadados": {
+                                "nextcloud": {"file_id": nc["file_id"], "etag": nc["etag"],
+                                              "content_type": nc["content_type"], "size": nc["size"],
+                                              "last_modified": nc["last_modified"]},
+                                "image": image_md,
+                                "sync": {"sync_method": self.SYNC_METHOD, "sync_timestamp": now.isoformat()},
+                            },
+                            "existe_no_nextcloud": True,
+                            "data_proc": now,
+                            "data_sinc": now,
+                            "id_cnj": conjunto_id,
+                        })
+                        stats["created"] += 1
+                    except DuplicateKeyError:
+                        self.db.rollback()
+                        if self.db.get(content_hash) is None:
+                            logger.debug("hash %s not found after duplicate-key error", content_hash[:16])
+                            continue
+                        self.db.update(content_hash, {"nome_img": info.get("name", ""), "caminho_img": info.get("path", ""),
+                                                      "existe_no_nextcloud": True, "data_sinc": now})
+                        stats["updated"] += 1
+                else:
+                    md = row.get("metadados")
+                    if md:
+                        if "nextcloud" in md:
+                            md["nextcloud"].update(self._nextcloud_meta(info, full=False))
+                        else:
+                            md["nextcloud"] = self._nextcloud_meta(info, full=True)
+                        md["sync"] = {"sync_method": self.SYNC_METHOD, "sync_timestamp": now.isoformat()}
+                    self.db.update(content_hash, {
+                        "nome_img": info.get("name", ""),
+                        "caminho_img": info.get("path", ""),
+                        "existe_no_nextcloud": True,
+                        "data_sinc": now,
+                        "metadados": md,
+                    })
+                    stats["updated"] += 1
+                stats["processed"] += 1
+            except Exception as e:  # noqa: BLE001 - one image never aborts the batch
+                logger.debug("failed to apply %s: %s", info.get("name", "unknown"), e)
+                self.db.rollback()
+                continue
+        return stats
+
+    def _thumbnails(self, prefetched: Optional[FeederBatch], decision):
+        """256x256 thumbnails of the images about to be INSERTED (decoded pixels come from
+        the feeder), one device call for the batch; written back through ``ImageStore.put_thumbnail`` and referenced
+        from ``metadados['image']['thumb']`` in arrival order.  ``None`` entries: no decoded pixels."""
+        n = len(decision.hashes)
+        out = [None] * n
+        if prefetched is None or not hasattr(self.db, "put_thumbnail"):
+            return out
+        idx = [i for i in range(n) if decision.hashes[i] and decision.is_new[i] and i < len(prefetched.rgb) and prefetched.rgb[i] is not None]
+        if idx:
+            t, _ = hostapi.thumbnails([prefetched.rgb[i] for i in idx], 256, 256, want_preview=False, device=self.device)
+            for j, i in enumerate(idx):
+                out[i] = t[j]
+        return out
 
     def sync_images_in_folder(self, folder_path: str, conjunto_id) -> Dict[str, int]:
         """The batch loop of the reference (:273-283).  Marking removed images (:286) is
@@ -173,9 +218,10 @@ class WebDAVSync:
         try:
             items = self.client.list_folder(folder_path, depth=1)
             images = self.client.filter_images(items)
-            if self.download_workers > 1:
+            if self.download_workers > 1 or self.store_thumbnails:
                 feeder = DownloadDecodeFeeder(self._fetch, self._validate_image, self.batch_size,
-                                              self.download_workers, prefetch_batches=self.prefetch_batches)
+                                              self.download_workers, prefetch_batches=self.prefetch_batches,
+                                              decode=self.store_thumbnails)
                 batches = ((fb.infos, fb) for fb in feeder.batches(images))
             else:
                 batches = ((images[i:i + self.batch_size], None) for i in range(0, len(images), self.batch_size))

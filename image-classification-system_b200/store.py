@@ -15,6 +15,12 @@ import uuid
 from typing import Dict, Iterable, List, Optional, Protocol
 
 
+class DuplicateKeyError(KeyError):
+    """``insert`` met a row with the same primary key: a concurrent writer got there first — what SQLAlchemy
+    reports as ``IntegrityError`` on flush (webdav_sync.py:355, activity_api_sync.py:875).  The caller rolls back
+    and takes the merge branch."""
+
+
 class ImageStore(Protocol):
     def get(self, content_hash: str) -> Optional[Dict]: ...
     def get_many(self, content_hashes: Iterable[str]) -> Dict[str, Dict]: ...
@@ -23,6 +29,8 @@ class ImageStore(Protocol):
     def commit(self) -> None: ...
     def rollback(self) -> None: ...
     def folder_for(self, file_id: str, name: str, path: str, now) -> Optional[Dict]: ...
+    # optional (SURVEY 8(f) rank 2 iii): thumbnails keyed by content hash, written in arrival order
+    # def put_thumbnail(self, content_hash: str, thumb_u8_hwc) -> str: ...   returns the reference stored in metadados
 
 
 class DictImageStore:
@@ -31,6 +39,7 @@ class DictImageStore:
     def __init__(self, rows: Optional[Dict[str, Dict]] = None):
         self.rows: Dict[str, Dict] = rows if rows is not None else {}
         self.folders: Dict[str, Dict] = {}
+        self.thumbs: Dict[str, "object"] = {}                 # side table keyed by content_hash
         self.commits = 0
         self._lock = threading.Lock()
 
@@ -44,7 +53,7 @@ class DictImageStore:
     def insert(self, row: Dict) -> None:
         with self._lock:
             if row["content_hash"] in self.rows:
-                raise KeyError(f"duplicate primary key {row['content_hash']}")
+                raise DuplicateKeyError(f"duplicate primary key {row['content_hash']}")
             self.rows[row["content_hash"]] = row
 
     def update(self, content_hash: str, fields: Dict) -> None:
@@ -67,6 +76,12 @@ class DictImageStore:
                     "imagens_sincronizadas": False, "existe_no_nextcloud": True, "data_proc": now, "data_sinc": now,
                 }
             return f
+
+    def put_thumbnail(self, content_hash: str, thumb) -> str:
+        """Side table ``thumbnails(content_hash PRIMARY KEY, h, w, pixels)``: last write wins, like nome_img."""
+        import numpy as np
+        self.thumbs[content_hash] = np.array(thumb, copy=True)
+        return f"thumbnails/{content_hash}"
 
     def sorted_hashes(self) -> List[str]:
         return sorted(self.rows)

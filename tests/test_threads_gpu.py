@@ -63,3 +63,36 @@ def test_five_threads_every_entry_point():
         t.join(timeout=300)
     assert not any(t.is_alive() for t in threads), "a worker hung"
     assert not errors, errors
+
+
+def test_concurrent_single_file_hashes_share_launches():
+    """The reference's call sites hash ONE file per call (webdav_sync.py:59, activity_api_sync.py:798, images.py:62) from
+    up to five service threads: concurrent calls are merged into shared device launches, results stay per caller."""
+    import hashlib
+
+    from ics_b200 import hostapi
+    hostapi.hash_batch([b"warm-up"])
+    c = hostapi._coalescers[hostapi.init(None)]
+    calls0, launches0 = c.calls, c.launches
+    errors: list = []
+
+    def worker(t):
+        try:
+            rng = np.random.default_rng(t)
+            for i in range(40):
+                blob = bytes(rng.integers(0, 256, size=int(rng.integers(1, 300_000)), dtype=np.uint8))
+                assert hostapi.hash_batch([blob]) == [hashlib.sha256(blob).hexdigest()]
+        except BaseException as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(5)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert c.calls - calls0 == 200
+    assert c.launches - launches0 < 200                     # some launches carried several callers' files
+    with pytest.raises(Exception):
+        hostapi.hash_batch([None])                          # an error reaches the caller that caused it
+    assert hostapi.hash_batch([b"abc"]) == ["ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"]

@@ -15,7 +15,7 @@ for path in sys.argv[1:]:
             print(f"  kernel {k}: {v['ms_per_launch']:.4f} ms  {v['achieved']:.0f} GB/s  frac {v['frac']:.3f}")
     if "e2e" in d:
         e = d["e2e"]
-        print(f"  e2e {e['value']:.0f} img/s  {e['h2d_gbs']:.1f} GB/s H2D  raw ceiling {e['raw_h2d']['aggregate_gbs']:.1f} GB/s"
+        print(f"  e2e {e['value']:.0f} img/s  {e['h2d_gbs']:.1f} GB/s H2D  raw ceiling {e['raw_h2d']['aggregate_gbs']:.1f} / mix {e['raw_h2d'].get('with_d2h_mix_aggregate_gbs', 0):.1f} GB/s"
               f"  frac {e['frac_of_raw_h2d']:.3f}  parity {e['parity']}")
     if "labels" in d:
         la = d["labels"]
