@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb2ingest.so")
+LIB_PATH = os.environ.get("B2_LIB_PATH") or os.path.join(HERE, "libb2ingest.so")   # B2_LIB_PATH: A/B builds of the library
 
 B2_OK = 0
 B2_ERR_BAD_ARG = -1
