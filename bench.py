@@ -812,18 +812,50 @@ def run_graft(args):
         del pick, uni
         l_act = (torch.rand(rows, device=dev, generator=gl) < 0.95).to(torch.uint8)
         l_counts = torch.empty((LABEL_IMAGES, LABEL_K), dtype=torch.int32, device=dev)
-        l_vec = torch.empty(vec_len, dtype=torch.int64, device=dev)
+        l_vecs = [torch.empty(vec_len, dtype=torch.int64, device=dev) for _ in range(2)]
+        l_vec = l_vecs[0]
         l_local = torch.empty(vec_len, dtype=torch.int64, device=dev)
+        comm_stream = torch.cuda.Stream(dev)
+        tallied = [torch.cuda.Event() for _ in range(2)]
+        reduced = [torch.cuda.Event() for _ in range(2)]
+        flip = {"i": 0}
 
         def label_step():
+            # tally on the main stream, the all-reduce of its partials on a second stream: the ~15 us NCCL latency of step i
+            # hides under the tally of step i+1 (two partial buffers); every step still produces its all-reduced vector
+            i = flip["i"]
+            flip["i"] ^= 1
+            main = torch.cuda.current_stream()
+            main.wait_event(reduced[i])                       # buffer i: its previous all-reduce is done
             engine.label_tally_device(l_img, l_cls, l_act, LABEL_IMAGES, LABEL_K, 0, True, l_counts,
-                                      l_vec[:LABEL_K + 7], l_vec[LABEL_K + 7:])
-            b2dist.allreduce_partials(l_vec)
+                                      l_vecs[i][:LABEL_K + 7], l_vecs[i][LABEL_K + 7:])
+            if world > 1:
+                tallied[i].record(main)
+                comm_stream.wait_event(tallied[i])
+                with torch.cuda.stream(comm_stream):
+                    b2dist.allreduce_partials(l_vecs[i])
+                    reduced[i].record(comm_stream)
             launches["n"] += 1
 
+        def label_drain():
+            torch.cuda.current_stream().wait_stream(comm_stream)
+
         label_steps = max(args.steps, 20)
-        ms_labels, _, _ = timed(label_step, label_steps, max(args.warmup, 3))
+        for _ in range(3):
+            label_step()
+        label_drain()
+        barrier()
+        le0, le1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches["n"] = 0
+        le0.record()
+        for _ in range(label_steps):
+            label_step()
+        label_drain()
+        le1.record()
+        barrier()
+        ms_labels = reduce_ranks(le0.elapsed_time(le1))
         label_launches = launches["n"]
+        l_vec = l_vecs[flip["i"] ^ 1]                          # the vector of the last step
         rows_per_s = rows * world * label_steps / (ms_labels / 1e3)
         engine.label_tally_device(l_img, l_cls, l_act, LABEL_IMAGES, LABEL_K, 0, True, l_counts,
                                   l_local[:LABEL_K + 7], l_local[LABEL_K + 7:])
@@ -948,7 +980,8 @@ def build_line(args, out, world, warmup, hbm_peak, peak_src, torch, dev):
                           "ms_per_step": lab["ms"] / lab["steps"], "gpu_launches": lab["launches"],
                           "roofline": kernels["tally_slab_kernel"], "kappa_general": lab["kappa_g"],
                           "partials_ok": bool(lab["label_ok"]),
-                          "collective": "b2_allreduce_i64 (NCCL) of k+7+1024 int64 on the tally's stream" if world > 1 else None,
+                          "collective": "b2_allreduce_i64 (NCCL) of k+7+1024 int64 on a second stream: the all-reduce of step i overlaps "
+                                        "the tally of step i+1 (two partial buffers)" if world > 1 else None,
                           "shuffled_rows": {"value": lab["rows"] / (lab["ms_scatter"] / 1e3), "unit": "rows/s per GPU",
                                             "ms_per_launch": lab["ms_scatter"],
                                             "path": "memset + tally_scatter_kernel (global RED.ADD) + fleiss_partials_kernel",

@@ -6,9 +6,9 @@
 The pipeline itself is native: ``b2_ingest_ring_*`` in ``csrc/ring.cu`` (C ABI, host pointers only).  SHA-256 is
 serial per message — one message moves at ~60 MB/s whatever else the GPU does — so PCIe (55 GB/s) is only kept
 busy when about a thousand messages hash at once.  The ring therefore bounds its depth in BYTES: a device staging
-ring of tens of GB carved into chunks of consecutive listing entries; each chunk is one H2D burst, one hash launch
-on one of 96 streams, one resize launch per shape, one read-back per output kind straight into the listing-order
-slots of the caller's buffers; ``submit`` blocks only while the ring is full, listings complete independently
+ring of tens of GB carved into chunks of consecutive listing entries; each chunk is one H2D burst, one resize launch
+per shape and one read-back per output kind straight into the listing-order slots of the caller's buffers; every ~4 GiB
+of chunks is ONE hash launch; ``submit`` blocks only while the ring is full, listings complete independently
 (``wait`` / ``poll``).  Any mix of image sizes (BASELINE config 3) goes through the same ring.
 
 This module only wraps the C calls: it allocates the page-locked result buffers (``b2_host_alloc``) and keeps
