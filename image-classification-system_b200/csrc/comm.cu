@@ -26,6 +26,7 @@ struct NcclApi {
     void *handle = nullptr;
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitRankConfig) CommInitRankConfig = nullptr;   // optional (NCCL >= 2.14)
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
@@ -65,6 +66,7 @@ static NcclApi *nccl_api() {
         B2_SYM(GetErrorString, "ncclGetErrorString");
         B2_SYM(GetVersion, "ncclGetVersion");
 #undef B2_SYM
+        api.CommInitRankConfig = reinterpret_cast<decltype(api.CommInitRankConfig)>(dlsym(h, "ncclCommInitRankConfig"));
         if (!ok) {
             snprintf(api.error, sizeof(api.error), "libnccl.so.2 lacks a required symbol");
             api.handle = nullptr;
@@ -151,7 +153,20 @@ extern "C" int b2_comm_init(int device, int rank, int world, const uint8_t *id, 
     c->device = device; c->rank = rank; c->world = world;
     ncclUniqueId uid;
     memcpy(&uid, id, sizeof(uid));
-    ncclResult_t r = api->CommInitRank(&c->comm, world, uid, rank);
+    // The exchanges of this path are tiny (8.6 KB of partials, 32 bytes per image of digests): a communicator of at
+    // most two CTAs keeps NCCL's kernel off the SMs the tally / hash kernels running beside it need (the default claims
+    // up to 32 CTAs and pushed the overlapped tally into a second wave).  B2_NCCL_MAX_CTAS overrides; 0 = NCCL's default.
+    int max_ctas = 2;
+    if (const char *e = getenv("B2_NCCL_MAX_CTAS")) max_ctas = atoi(e);
+    ncclResult_t r;
+    if (api->CommInitRankConfig && max_ctas > 0) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = max_ctas;
+        r = api->CommInitRankConfig(&c->comm, world, uid, rank, &cfg);
+    } else {
+        r = api->CommInitRank(&c->comm, world, uid, rank);
+    }
     if (r != ncclSuccess) {
         delete c;
         return fail(B2_ERR_NCCL, "ncclCommInitRank failed: %s", api->GetErrorString(r));
