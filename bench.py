@@ -724,39 +724,60 @@ def run_graft(args):
         c_counts = torch.empty((img_hi - img_lo, LABEL_K), dtype=torch.int32, device=dev)
         vec = torch.empty(vec_len, dtype=torch.int64, device=dev)
 
-        def c4_step():
+        def c4_step_nccl():
             engine.label_tally_device(d_img, d_cls, d_act, img_hi - img_lo, LABEL_K, img_lo, True, c_counts,
                                       vec[:LABEL_K + 7], vec[LABEL_K + 7:])
-            b2dist.allreduce_partials(vec)                   # b2_allreduce_i64 on the same stream (no clone, no sync)
+            b2dist.allreduce_partials(vec)                   # b2_allreduce_i64 (NCCL) on the same stream
 
-        # tally + all-reduce captured in ONE CUDA graph of `inner` steps: at 12.5 M rows per GPU the tally is ~20 us,
-        # launch gaps would dominate otherwise
+        fused = world > 1
+        if fused:
+            comm.enable_peer_reduce(vec_len)                 # mailboxes in every rank's HBM, mapped by its peers (CUDA IPC)
+
+        def c4_step_fused():
+            # ONE kernel: the slab tally whose last CTA all-reduces partials + histogram over NVLink peer memory
+            comm.label_tally_reduce(d_img, d_cls, d_act, img_hi - img_lo, LABEL_K, img_lo, c_counts, vec)
+
+        # `inner` steps captured in ONE CUDA graph: at 12.5 M rows per GPU the tally is ~30 us, launch gaps would
+        # dominate otherwise
         inner = 20
-        cap_stream = torch.cuda.Stream(dev)
-        graph, graphed = torch.cuda.CUDAGraph(), False
-        c4_step()
-        torch.cuda.synchronize()
-        try:
-            with torch.cuda.stream(cap_stream):
-                c4_step()
-                cap_stream.synchronize()
-                with torch.cuda.graph(graph, stream=cap_stream):
-                    for _ in range(inner):
-                        c4_step()
-            graphed = True
-        except Exception as e:  # noqa: BLE001 - report and fall back to plain launches
-            graph_err = repr(e)[:200]
-            torch.cuda.synchronize()
-
-        def c4_outer():
-            if graphed:
-                graph.replay()
-            else:
-                for _ in range(inner):
-                    c4_step()
-
         outer = max(args.steps, 5)
-        ms_c4, _, _ = timed(c4_outer, outer, 3)
+
+        def run_graphed(step):
+            cap_stream = torch.cuda.Stream(dev)
+            graph, graphed, err = torch.cuda.CUDAGraph(), False, None
+            step()
+            torch.cuda.synchronize()
+            try:
+                with torch.cuda.stream(cap_stream):
+                    step()
+                    cap_stream.synchronize()
+                    with torch.cuda.graph(graph, stream=cap_stream):
+                        for _ in range(inner):
+                            step()
+                graphed = True
+            except Exception as e:  # noqa: BLE001 - report and fall back to plain launches
+                err = repr(e)[:200]
+                torch.cuda.synchronize()
+
+            def outer_step():
+                if graphed:
+                    graph.replay()
+                else:
+                    for _ in range(inner):
+                        step()
+
+            ms, _, _ = timed(outer_step, outer, 3)
+            torch.cuda.synchronize()
+            return ms, graphed, err, graph
+
+        ms_nccl, graphed_nccl, graph_err, _g1 = run_graphed(c4_step_nccl)
+        got_nccl = vec.cpu().numpy()
+        if fused:
+            ms_c4, graphed, graph_err2, _g2 = run_graphed(c4_step_fused)
+            graph_err = graph_err or graph_err2
+            peer_timeout = comm.peer_timed_out()
+        else:
+            ms_c4, graphed, peer_timeout = ms_nccl, graphed_nccl, False
         torch.cuda.synchronize()
         got = vec.cpu().numpy()
         ms_tally_local = kernel_ms(lambda: engine.label_tally_device(d_img, d_cls, d_act, img_hi - img_lo, LABEL_K, img_lo, True,
@@ -773,6 +794,7 @@ def run_graft(args):
             p_ref, h_ref = numpy_tally_partials(f_img, f_cls, f_act, 0, LABEL_IMAGES, LABEL_K)
             cpu_rows_per_s = f_img.size / (time.perf_counter() - t0)
             ok4 = bool(np.array_equal(got[:LABEL_K + 7], p_ref) and np.array_equal(got[LABEL_K + 7:], h_ref))
+            ok4 = ok4 and bool(np.array_equal(got, got_nccl)) and not peer_timeout
             del f_img, f_cls, f_act
         digest = hashlib.sha256(got.tobytes()).hexdigest()
         kappa_g = b2labels.fleiss_kappa_from_hist(got[:LABEL_K], int(got[LABEL_K + 1]), int(got[LABEL_K + 3]), got[LABEL_K + 7:])
@@ -784,6 +806,9 @@ def run_graft(args):
                                  "tally + b2_allreduce_i64 (NCCL) of k+7 partials and the 1024-bin agreement histogram",
                      "rows_per_gpu": rows_local, "value": rows_total * outer * inner / (ms_c4 / 1e3), "unit": "rows/s",
                      "us_per_step": 1e3 * ms_c4 / (outer * inner), "steps": outer * inner, "cuda_graph": graphed,
+                     "collective": ("fused into the tally kernel: its last CTA all-reduces the 8.6 KB vector over NVLink peer memory "
+                                    "(b2_label_tally_reduce; CUDA IPC mailboxes, no NCCL call)") if fused else None,
+                     "us_per_step_tally_then_nccl_allreduce": 1e3 * ms_nccl / (outer * inner) if fused else None,
                      "tally_kernel_us": 1e3 * ms_tally_local,
                      "roofline": {"bound": "hbm", "achieved": c4_bytes / (ms_tally_local / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                   "frac": c4_bytes / (ms_tally_local / 1e3) / 1e9 / hbm_peak, "algorithmic_bytes": c4_bytes},
@@ -795,10 +820,10 @@ def run_graft(args):
                                    "when every image has exactly 100 active ratings",
                      "partials_sha256": digest, "numpy_rows_per_s_1_thread": cpu_rows_per_s,
                      "parity": {"ok": all_ok(ok4), "checked": "all k+7 partials and 1024 histogram bins equal NumPy's over the whole "
-                                                              "table (rank 0); identical integers at every N => identical kappa"}}
-        if not graphed:
+                                                              "table (rank 0) and the NCCL path's; identical integers at every N => identical kappa"}}
+        if graph_err:
             out["c4"]["cuda_graph_error"] = graph_err
-        del d_img, d_cls, d_act, c_counts, graph
+        del d_img, d_cls, d_act, c_counts, _g1
         torch.cuda.empty_cache()
 
     if want("labels"):
@@ -816,6 +841,8 @@ def run_graft(args):
         l_vec = l_vecs[0]
         l_local = torch.empty(vec_len, dtype=torch.int64, device=dev)
         comm_stream = torch.cuda.Stream(dev)
+        if world > 1:
+            comm.enable_peer_reduce(vec_len)
         tallied = [torch.cuda.Event() for _ in range(2)]
         reduced = [torch.cuda.Event() for _ in range(2)]
         flip = {"i": 0}
@@ -833,9 +860,9 @@ def run_graft(args):
                 tallied[i].record(main)
                 comm_stream.wait_event(tallied[i])
                 with torch.cuda.stream(comm_stream):
-                    b2dist.allreduce_partials(l_vecs[i])
+                    comm.peer_allreduce_i64(l_vecs[i])        # one-CTA kernel over NVLink peer memory (no NCCL call)
                     reduced[i].record(comm_stream)
-            launches["n"] += 1
+            launches["n"] += 1 if world == 1 else 2
 
         def label_drain():
             torch.cuda.current_stream().wait_stream(comm_stream)
@@ -980,8 +1007,8 @@ def build_line(args, out, world, warmup, hbm_peak, peak_src, torch, dev):
                           "ms_per_step": lab["ms"] / lab["steps"], "gpu_launches": lab["launches"],
                           "roofline": kernels["tally_slab_kernel"], "kappa_general": lab["kappa_g"],
                           "partials_ok": bool(lab["label_ok"]),
-                          "collective": "b2_allreduce_i64 (NCCL) of k+7+1024 int64 on a second stream: the all-reduce of step i overlaps "
-                                        "the tally of step i+1 (two partial buffers)" if world > 1 else None,
+                          "collective": "b2_peer_allreduce_i64 (one CTA, NVLink peer memory) of k+7+1024 int64 on a second stream: the "
+                                        "all-reduce of step i overlaps the tally of step i+1 (two partial buffers)" if world > 1 else None,
                           "shuffled_rows": {"value": lab["rows"] / (lab["ms_scatter"] / 1e3), "unit": "rows/s per GPU",
                                             "ms_per_launch": lab["ms_scatter"],
                                             "path": "memset + tally_scatter_kernel (global RED.ADD) + fleiss_partials_kernel",

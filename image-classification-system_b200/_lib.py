@@ -105,6 +105,11 @@ SIGNATURES = {
     "b2_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2_allgather_digests": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp]),
     "b2_allreduce_i64": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
+    "b2_comm_enable_peer_reduce": (C.c_int, [_vp, C.c_uint32]),
+    "b2_comm_peer_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "b2_peer_allreduce_i64": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
+    "b2_label_tally_reduce": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                        _vp, _vp, _vp]),
     "b2_dedupe_global_workspace_bytes": (C.c_uint64, [C.c_uint32, C.c_uint32]),
     "b2_dedupe_global": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, C.c_uint64, _vp, _vp, _vp, _vp,
                                    _vp, C.c_uint64, _vp]),

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 
 namespace b2 {
 
@@ -125,6 +126,11 @@ static GlobalLayout global_layout(uint32_t world, uint32_t n_max) {
 struct b2_comm {
     ncclComm_t comm = nullptr;
     int device = 0, rank = 0, world = 1;
+    // peer reduce (b2_comm_enable_peer_reduce): my mailbox, the peers' mapped through CUDA IPC, the device descriptor
+    b2::PeerReduceDesc *d_peer = nullptr;
+    uint8_t *d_mailbox = nullptr;
+    void *peer_maps[b2::kPeerMaxWorld] = {};
+    uint32_t peer_cap = 0;
 };
 
 extern "C" int b2_comm_unique_id(uint8_t *id_out) {
@@ -179,10 +185,15 @@ extern "C" int b2_comm_destroy(b2_comm *c) {
     using namespace b2;
     if (!c) return B2_OK;
     NcclApi *api = nccl_api();
-    if (api && c->comm) {
-        cudaSetDevice(c->device);
-        api->CommDestroy(c->comm);
+    cudaSetDevice(c->device);
+    if (c->d_peer) {
+        cudaDeviceSynchronize();
+        for (int q = 0; q < c->world; ++q)
+            if (c->peer_maps[q]) cudaIpcCloseMemHandle(c->peer_maps[q]);
+        cudaFree(c->d_peer);
+        cudaFree(c->d_mailbox);
     }
+    if (api && c->comm) api->CommDestroy(c->comm);
     delete c;
     return B2_OK;
 }
@@ -271,4 +282,111 @@ extern "C" int b2_dedupe_global(b2_comm *c, const uint8_t *d_digests, const uint
         B2_LAUNCH_CHECK("global_slice_kernel");
     }
     return B2_OK;
+}
+
+// ---- all-reduce over NVLink peer memory, fused into the tally ------------------------------------------------------
+namespace b2 {
+int label_tally_impl(const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
+                     uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
+                     int32_t *d_counts, int64_t *d_partials, int64_t *d_agree_hist, PeerReduceDesc *peer, void *stream);
+
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(PeerReduceDesc *d, unsigned long long *vec, uint32_t n) {
+    peer_allreduce_cta(d, vec, n);
+}
+}  // namespace b2
+
+// Collective and blocking (every rank calls it once, with the same max_values): allocates this rank's mailbox, exchanges
+// the CUDA IPC handles through the communicator and maps the peers' mailboxes.  One process per GPU, all GPUs of one box
+// with peer access (NVLink / NVSwitch).
+extern "C" int b2_comm_enable_peer_reduce(b2_comm *c, uint32_t max_values) {
+    using namespace b2;
+    B2_REQUIRE(c != nullptr && max_values >= 1 && max_values <= (1u << 20), "b2_comm_enable_peer_reduce: bad argument");
+    B2_REQUIRE(c->world <= kPeerMaxWorld, "b2_comm_enable_peer_reduce: at most %d ranks", kPeerMaxWorld);
+    if (c->d_peer) return c->peer_cap >= max_values ? B2_OK : fail(B2_ERR_BAD_ARG, "b2_comm_enable_peer_reduce: already enabled with a smaller capacity");
+    NcclApi *api = nccl_api();
+    if (!api) return fail(B2_ERR_NCCL, "b2_comm_enable_peer_reduce: NCCL is not available");
+    B2_CUDA_CHECK(cudaSetDevice(c->device));
+    const uint32_t cap = (max_values + 31u) & ~31u;
+    const size_t flag_bytes = 256, mail_bytes = size_t(2) * c->world * cap * 8;   // 2 x world flags fit 256 bytes (world <= 16)
+    B2_CUDA_CHECK(cudaMalloc(&c->d_mailbox, flag_bytes + mail_bytes));
+    B2_CUDA_CHECK(cudaMemset(c->d_mailbox, 0, flag_bytes + mail_bytes));
+    cudaIpcMemHandle_t mine;
+    B2_CUDA_CHECK(cudaIpcGetMemHandle(&mine, c->d_mailbox));
+    uint8_t *d_handles = nullptr;
+    B2_CUDA_CHECK(cudaMalloc(&d_handles, size_t(c->world + 1) * sizeof(mine)));
+    B2_CUDA_CHECK(cudaMemcpy(d_handles + size_t(c->world) * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    B2_NCCL_CHECK(api->AllGather(d_handles + size_t(c->world) * sizeof(mine), d_handles, sizeof(mine), ncclUint8, c->comm, nullptr));
+    B2_CUDA_CHECK(cudaStreamSynchronize(nullptr));
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    B2_CUDA_CHECK(cudaMemcpy(all.data(), d_handles, size_t(c->world) * sizeof(mine), cudaMemcpyDeviceToHost));
+    B2_CUDA_CHECK(cudaFree(d_handles));
+    PeerReduceDesc h = {};
+    h.world = c->world; h.rank = c->rank; h.cap = cap; h.epoch = 0; h.ticket = 0; h.error = 0;
+    for (int q = 0; q < c->world; ++q) {
+        uint8_t *base = c->d_mailbox;
+        if (q != c->rank) {
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                return fail(B2_ERR_CUDA, "b2_comm_enable_peer_reduce: cannot map the mailbox of rank %d: %s", q, cudaGetErrorString(e));
+            c->peer_maps[q] = p;
+            base = static_cast<uint8_t *>(p);
+        }
+        h.flags[q] = reinterpret_cast<uint32_t *>(base);
+        h.mail[q] = reinterpret_cast<unsigned long long *>(base + flag_bytes);
+    }
+    B2_CUDA_CHECK(cudaMalloc(&c->d_peer, sizeof(h)));
+    B2_CUDA_CHECK(cudaMemcpy(c->d_peer, &h, sizeof(h), cudaMemcpyHostToDevice));
+    c->peer_cap = cap;
+    // nobody writes into a mailbox before every rank has zeroed and mapped: one more (tiny) collective as a barrier
+    int64_t *d_one = reinterpret_cast<int64_t *>(c->d_mailbox + flag_bytes);
+    B2_NCCL_CHECK(api->AllReduce(d_one, d_one, 1, ncclInt64, ncclSum, c->comm, nullptr));
+    B2_CUDA_CHECK(cudaStreamSynchronize(nullptr));
+    return B2_OK;
+}
+
+// 1 = a peer did not arrive within the spin budget of some earlier peer collective (results of that step are invalid).
+extern "C" int b2_comm_peer_status(b2_comm *c, int *timed_out) {
+    using namespace b2;
+    B2_REQUIRE(c != nullptr && timed_out != nullptr && c->d_peer != nullptr, "b2_comm_peer_status: peer reduce is not enabled");
+    PeerReduceDesc h;
+    B2_CUDA_CHECK(cudaMemcpy(&h, c->d_peer, sizeof(h), cudaMemcpyDeviceToHost));
+    *timed_out = int(h.error);
+    return B2_OK;
+}
+
+extern "C" int b2_peer_allreduce_i64(b2_comm *c, int64_t *d_values, uint32_t count, void *stream) {
+    using namespace b2;
+    B2_REQUIRE(c != nullptr && c->d_peer != nullptr, "b2_peer_allreduce_i64: call b2_comm_enable_peer_reduce first");
+    B2_REQUIRE(count == 0 || d_values != nullptr, "b2_peer_allreduce_i64: null pointer");
+    B2_REQUIRE(count <= c->peer_cap, "b2_peer_allreduce_i64: %u values exceed the mailbox capacity %u", count, c->peer_cap);
+    if (count == 0) return B2_OK;
+    // Same L1 / shared-memory split as the tally kernel it usually runs beside: an SM only changes its carve-out when
+    // idle, so a kernel with another preference would keep one SM away from the tally's two-CTAs-per-SM wave.
+    static std::once_flag once[64];
+    std::call_once(once[c->device & 63], [] {
+        cudaFuncSetAttribute(peer_allreduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    });
+    peer_allreduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(c->d_peer, reinterpret_cast<unsigned long long *>(d_values), count);
+    B2_LAUNCH_CHECK("peer_allreduce_kernel");
+    return B2_OK;
+}
+
+extern "C" int b2_label_tally_reduce(b2_comm *c, const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
+                                     uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
+                                     int32_t *d_counts, int64_t *d_partials_hist, void *stream) {
+    using namespace b2;
+    B2_REQUIRE(c != nullptr && d_partials_hist != nullptr, "b2_label_tally_reduce: null pointer");
+    const uint32_t n_values = k + B2_PARTIALS_EXTRA + B2_AGREE_BINS;
+    if (c->world == 1)
+        return b2_label_tally(d_image_idx, d_class_idx, d_active, rows, image_base, n_images, k, flags, d_counts, d_partials_hist,
+                              d_partials_hist + k + B2_PARTIALS_EXTRA, stream);
+    if (c->d_peer != nullptr && (flags & B2_TALLY_SORTED) && n_values <= c->peer_cap)
+        return label_tally_impl(d_image_idx, d_class_idx, d_active, rows, image_base, n_images, k, flags, d_counts, d_partials_hist,
+                                d_partials_hist + k + B2_PARTIALS_EXTRA, c->d_peer, stream);
+    // any-order rows or no peer mailbox: the tally, then NCCL
+    int rc = b2_label_tally(d_image_idx, d_class_idx, d_active, rows, image_base, n_images, k, flags, d_counts, d_partials_hist,
+                            d_partials_hist + k + B2_PARTIALS_EXTRA, stream);
+    if (rc != B2_OK) return rc;
+    return b2_allreduce_i64(c, d_partials_hist, n_values, stream);
 }

@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(kSlabThreads, 2)
 tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restrict__ class_idx,
                   const uint8_t *__restrict__ active, uint64_t rows, int32_t image_base, uint32_t n_images,
                   uint32_t k, uint32_t tile_log2, int32_t *__restrict__ counts,
-                  unsigned long long *__restrict__ g_partials, unsigned long long *__restrict__ g_hist) {
+                  unsigned long long *__restrict__ g_partials, unsigned long long *__restrict__ g_hist,
+                  PeerReduceDesc *__restrict__ peer) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t T = 1u << tile_log2, tmask = T - 1u;
     uint8_t *ring = smem_raw;
@@ -565,6 +566,19 @@ tally_slab_kernel(const int32_t *__restrict__ image_idx, const uint8_t *__restri
     __syncthreads();
     commit_partials(part, class_tot, k, g_partials);
     if (kHist) commit_hist32(hist, g_hist);
+    // Fused collective (b2_label_tally_reduce): the CTA that finishes last all-reduces partials + histogram (one
+    // contiguous vector: g_hist == g_partials + k + 7) over NVLink peer memory, in this same kernel.
+    if (kHist && peer != nullptr) {
+        __shared__ uint32_t s_last;
+        __threadfence();                                          // my atomics are visible before I take a ticket
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(&peer->ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            peer_allreduce_cta(peer, g_partials, k + uint32_t(B2_PARTIALS_EXTRA) + kAgreeBins);
+        }
+    }
 }
 
 // Any row order: one RED.ADD per active row into a zeroed count matrix.
@@ -675,10 +689,26 @@ extern "C" uint64_t b2_fleiss_workspace_bytes(uint32_t n_images) {
     return 16 + 8ull * b2::kFleissGridMax;
 }
 
+namespace b2 {
+int label_tally_impl(const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
+                     uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
+                     int32_t *d_counts, int64_t *d_partials, int64_t *d_agree_hist, PeerReduceDesc *peer, void *stream);
+}
+
 extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
                               uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
                               int32_t *d_counts, int64_t *d_partials, int64_t *d_agree_hist, void *stream) {
+    return b2::label_tally_impl(d_image_idx, d_class_idx, d_active, rows, image_base, n_images, k, flags, d_counts, d_partials,
+                                d_agree_hist, nullptr, stream);
+}
+
+// `peer` != NULL (sorted mode, histogram contiguous behind the partials): the slab kernel all-reduces its own result.
+int b2::label_tally_impl(const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
+                         uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
+                         int32_t *d_counts, int64_t *d_partials, int64_t *d_agree_hist, PeerReduceDesc *peer, void *stream) {
     using namespace b2;
+    B2_REQUIRE(peer == nullptr || ((flags & B2_TALLY_SORTED) && d_agree_hist == d_partials + k + B2_PARTIALS_EXTRA),
+               "b2_label_tally_reduce: needs B2_TALLY_SORTED and the histogram right behind the partials");
     B2_REQUIRE(d_counts && d_partials, "b2_label_tally: null output pointer");
     B2_REQUIRE((reinterpret_cast<uintptr_t>(d_agree_hist) & 7) == 0, "b2_label_tally: misaligned histogram");
     B2_REQUIRE(k >= 1 && k <= 256, "b2_label_tally: k must be in 1..256 (class_idx is uint8)");
@@ -719,7 +749,7 @@ extern "C" int b2_label_tally(const int32_t *d_image_idx, const uint8_t *d_class
                         uint32_t(want), smem_slab, t, hist != nullptr, occ);
             }
             kern<<<uint32_t(want), kSlabThreads, smem_slab, st>>>(d_image_idx, d_class_idx, d_active, rows,
-                                                                 int32_t(image_base), n_images, k, t, d_counts, partials, hist);
+                                                                 int32_t(image_base), n_images, k, t, d_counts, partials, hist, peer);
             B2_LAUNCH_CHECK("tally_slab_kernel");
             return B2_OK;
         };

@@ -147,6 +147,35 @@ class Comm:
         check(lib.b2_allreduce_i64(self._h, values.data_ptr(), values.numel(), self._stream(stream)))
         return values
 
+    # ---- the label all-reduce over NVLink peer memory, fused into the tally kernel ----
+    def enable_peer_reduce(self, max_values: int) -> None:
+        """``b2_comm_enable_peer_reduce``: collective, blocking, once — mailboxes in every rank's HBM mapped by its peers
+        through CUDA IPC."""
+        check(lib.b2_comm_enable_peer_reduce(self._h, int(max_values)))
+        self.peer_values = int(max_values)
+
+    def peer_timed_out(self) -> bool:
+        v = C.c_int()
+        check(lib.b2_comm_peer_status(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def peer_allreduce_i64(self, values, stream=None):
+        """In-place sum over ranks through the mailboxes (one small kernel, no NCCL call)."""
+        assert values.is_cuda and values.is_contiguous() and values.element_size() == 8
+        check(lib.b2_peer_allreduce_i64(self._h, values.data_ptr(), values.numel(), self._stream(stream)))
+        return values
+
+    def label_tally_reduce(self, image_idx, class_idx, active, n_images: int, k: int, image_base: int, counts, vec,
+                           sorted_by_image: bool = True, stream=None):
+        """``b2_label_tally_reduce``: the tally of this rank's rows whose kernel also all-reduces ``vec`` = int64[k + 7 +
+        B2_AGREE_BINS] (partials, then the agreement histogram) over the ranks; ``counts`` stays this rank's slab."""
+        assert vec.is_cuda and vec.is_contiguous() and vec.numel() == k + _lib.B2_PARTIALS_EXTRA + _lib.B2_AGREE_BINS
+        check(lib.b2_label_tally_reduce(self._h, image_idx.data_ptr(), class_idx.data_ptr(), active.data_ptr(),
+                                        image_idx.numel(), image_base, n_images, k,
+                                        _lib.B2_TALLY_SORTED if sorted_by_image else 0, counts.data_ptr(), vec.data_ptr(),
+                                        self._stream(stream)))
+        return counts, vec
+
     def allgather_digests(self, digests, stream=None):
         """uint8[n,32] on every rank (same n) -> uint8[world*n,32] in rank order."""
         import torch

@@ -287,6 +287,23 @@ int b2_allreduce_i64(b2_comm *c, int64_t *d_values, uint64_t count, void *stream
  * = listing position of the first / last occurrence of the same content (-1 = invalid entry); d_counts[3] =
  * {processed, created, updated} of the WHOLE listing (identical on every rank).  d_workspace: 256-byte aligned,
  * b2_dedupe_global_workspace_bytes(world, n_max) bytes. */
+/* The label all-reduce fused into the tally kernel ("fuse the partial reduction into the tally
+ * kernel epilogue").  The partial vector is 8.6 KB: an NCCL all-reduce of that size is pure latency (~30 us at eight
+ * ranks, as long as config 4's 12.5 M-row tally).  b2_comm_enable_peer_reduce (collective, blocking, once) gives
+ * every rank a mailbox in its own HBM that its peers map through CUDA IPC; b2_label_tally_reduce then runs the SAME
+ * slab kernel as b2_label_tally whose last CTA writes the rank's vector into every peer's mailbox over NVLink,
+ * publishes a flag, waits for the peers' flags and sums the slots in rank order — one kernel, no NCCL call, the same
+ * integers in the same order on every rank.  d_partials_hist: int64[k + B2_PARTIALS_EXTRA + B2_AGREE_BINS] (partials,
+ * then the agreement histogram), replaced by the sum over ranks; d_counts stays this rank's slab.  Needs
+ * B2_TALLY_SORTED; any-order rows (or a communicator without mailboxes) fall back to b2_label_tally +
+ * b2_allreduce_i64.  b2_peer_allreduce_i64: the same exchange for any int64 vector (one small kernel).  A peer that
+ * never arrives is given up after ~3 s (b2_comm_peer_status reports it); the kernels never hang. */
+int b2_comm_enable_peer_reduce(b2_comm *c, uint32_t max_values);
+int b2_comm_peer_status(b2_comm *c, int *timed_out);
+int b2_peer_allreduce_i64(b2_comm *c, int64_t *d_values, uint32_t count, void *stream);
+int b2_label_tally_reduce(b2_comm *c, const int32_t *d_image_idx, const uint8_t *d_class_idx, const uint8_t *d_active,
+                          uint64_t rows, uint32_t image_base, uint32_t n_images, uint32_t k, uint32_t flags,
+                          int32_t *d_counts, int64_t *d_partials_hist, void *stream);
 uint64_t b2_dedupe_global_workspace_bytes(uint32_t world, uint32_t n_max);
 int b2_dedupe_global(b2_comm *c, const uint8_t *d_digests, const uint8_t *d_valid, const uint32_t *d_seq,
                      uint32_t n_local, uint32_t n_max, const uint8_t *d_existing, uint64_t m,

@@ -87,6 +87,29 @@ assert np.array_equal(p[k + 7:], agreement_hist(counts_ref))
 assert np.array_equal(dcounts.cpu().numpy(), counts_ref[lo:hi])
 kg = labels.fleiss_kappa_from_hist(p[:k], int(p[k + 1]), int(p[k + 3]), p[k + 7:])
 assert abs(kg - fleiss_kappa_general(counts_ref)) <= 1e-12 * abs(kg)
+
+# ---- the same all-reduce over NVLink peer memory: standalone and fused into the tally kernel; many epochs (the
+# mailboxes alternate between two parities), a second vector size, and the NCCL result as the reference
+c.enable_peer_reduce(k + 7 + 1024)
+want = torch.from_numpy(p.copy()).cuda()
+for it in range(25):
+    v = torch.arange(37, dtype=torch.int64, device="cuda") * (rank + 1) + it
+    c.peer_allreduce_i64(v)
+    assert v.cpu().tolist() == [sum(i * (r + 1) + it for r in range(world)) for i in range(37)], it
+    buf2 = torch.empty(k + 7 + 1024, dtype=torch.int64, device="cuda")
+    dc2 = torch.empty((hi - lo, k), dtype=torch.int32, device="cuda")
+    c.label_tally_reduce(torch.from_numpy(img[r0:r1]).cuda(), torch.from_numpy(cls[r0:r1]).cuda(),
+                         torch.from_numpy(act[r0:r1]).cuda(), hi - lo, k, lo, dc2, buf2)
+    assert torch.equal(buf2, want), it
+    assert torch.equal(dc2, dcounts)
+# any-order rows: falls back to the scatter tally + NCCL, same integers except the two order-check entries
+perm = np.random.default_rng(3).permutation(r1 - r0)
+buf3 = torch.empty(k + 7 + 1024, dtype=torch.int64, device="cuda")
+c.label_tally_reduce(torch.from_numpy(img[r0:r1][perm]).cuda(), torch.from_numpy(cls[r0:r1][perm]).cuda(),
+                     torch.from_numpy(act[r0:r1][perm]).cuda(), hi - lo, k, lo, dc2, buf3, sorted_by_image=False)
+assert torch.equal(buf3[:k + 6], want[:k + 6]) and torch.equal(buf3[k + 7:], want[k + 7:])
+torch.cuda.synchronize()
+assert not c.peer_timed_out()
 c.close()
 print(json.dumps({"rank": rank, "kappa": repr(kg), "counts": counts.cpu().tolist()}))
 '''
