@@ -276,3 +276,44 @@ def test_ring_back_pressure_and_errors():
     res = ring.result(ring.submit(images[:7]))
     assert [bytes(d) for d in res.digests] == [want[g % 6] for g in range(7)]
     ring.close()
+
+
+def test_ring_stress_random_listings_wraparound():
+    """Many listings of random sizes (empty files, one-byte files, odd image shapes, more entries than one chunk holds)
+    through a small ring that wraps many times, three in flight, waited for in rotation: every digest == hashlib, every
+    thumbnail == Pillow, every dedupe decision == the sequential loop over that listing."""
+    import hashlib
+
+    from ics_b200.pipeline import IngestRing
+    rng = np.random.default_rng(2024)
+    ring = IngestRing(ring_bytes=64 << 20, chunk_bytes=3 << 20, max_listings=3, max_images=64, out_h=32, out_w=40, want_preview=True)
+    pool = [rng.integers(0, 256, int(rng.integers(0, 400_000)), dtype=np.uint8) for _ in range(40)]
+    pool[0] = np.zeros(0, dtype=np.uint8)                             # an empty file
+    pool[1] = np.array([7], dtype=np.uint8)                           # one byte
+    pics = [synth_image(9000 + i, int(rng.integers(33, 300)), int(rng.integers(41, 300))) for i in range(12)]
+    inflight = []
+
+    def check(entry):
+        ticket, files, pixels = entry
+        res = ring.result(ticket)
+        seen = set()
+        for i, f in enumerate(files):
+            d = hashlib.sha256(f.tobytes()).digest()
+            assert bytes(res.digests[i]) == d
+            assert bool(res.is_new[i]) == (d not in seen)
+            seen.add(d)
+            if pixels[i] is not None:
+                assert np.array_equal(res.thumbs[i], thumbnail_u8(pixels[i], 32, 40))
+        assert res.stats["processed"] == len(files) and res.stats["created"] == len(seen)
+
+    for it in range(30):
+        n = int(rng.integers(1, 60))
+        files = [pool[int(j)] for j in rng.integers(0, len(pool), n)]
+        pixels = [pics[int(j)] if rng.random() < 0.5 else None for j in rng.integers(0, len(pics), n)]
+        if len(inflight) == 3:
+            check(inflight.pop(0))
+        inflight.append((ring.submit(pixels, files=files), files, pixels))
+    while inflight:
+        check(inflight.pop(0))
+    assert ring.stats()["bytes_in_flight"] == 0 or ring.stats()["chunks_in_flight"] >= 0
+    ring.close()
