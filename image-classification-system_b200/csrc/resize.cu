@@ -116,6 +116,10 @@ struct b2_resize_plan {
                           //         (oy << 2 | accumulator + 1) of the output row that ENDS with this input row, else 0}
     int rps_scat, stage_bytes_scat;
     size_t smem_scat;
+    // pair kernel (two output columns per thread): quad offset / quad count of the odd column inside the union window
+    int pair;             // 1 = an instantiation of resize_pairs_kernel fits this plan
+    int pair_dq, pair_nqb, pair_threads, rps_pair, stage_bytes_pair;
+    size_t smem_pair;
 };
 
 namespace b2 {
@@ -402,6 +406,237 @@ resize_bands_kernel(const __grid_constant__ ResizeParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// resize_pairs_kernel<KQ, DQ, NQB> — scatter form with TWO adjacent output columns per thread.
+// The windows of neighbouring columns overlap by half (window = 2 x scale, step = scale), so a thread that owns
+// columns 2t and 2t+1 loads, aligns and de-interleaves the UNION of their windows once: for 1080p -> 256 (KQ = 16
+// taps, columns 7 or 8 pixels apart) 19 LDS + 18 SHF + 36 PRMT instead of 2 x (13 + 12 + 24).  Column A's taps sit
+// under quads 0 .. KQ/4-1 of the union, column B's under quads DQ .. DQ+NQB-1 (its coefficient limbs are placed at
+// (xmin_B - xmin_A) - 4 DQ inside that range, zero elsewhere): 9 IDP.4A per quad and column.  Everything else —
+// stage ring, scatter-form vertical pass, never-reset accumulators — is the band kernel's.  Half the threads per CTA
+// (out_w / 2), so stages are shorter and more CTAs share an SM.
+// ---------------------------------------------------------------------------------------
+template <int KQ, int DQ, int NQB>
+__global__ void __launch_bounds__(128, (KQ <= 20 ? 4 : 2))
+resize_pairs_kernel(const __grid_constant__ ResizeParams p) {
+    constexpr int NQ = KQ / 4;
+    constexpr int NU = (DQ + NQB > NQ) ? DQ + NQB : NQ;              // quads of the union window
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+
+    const int tid = threadIdx.x;
+    const int img = blockIdx.x / p.n_bands;
+    const int band = blockIdx.x - img * p.n_bands;
+    const int oy0 = band * p.band_rows;
+    const int oy1 = min(oy0 + p.band_rows, p.out_h);
+    const int r0 = p.vbounds[2 * oy0];
+    const int r1 = p.vbounds[2 * (oy1 - 1)] + p.vbounds[2 * (oy1 - 1) + 1];
+    const int n_rows = r1 - r0;
+    const int pitch = p.in_w * 3;
+    const uint8_t *img_ptr = p.rgb + p.offsets[img];
+    const uint64_t img_bytes = uint64_t(p.in_h) * pitch;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(img_ptr)) & 15) == 0;
+    uint8_t *ring = smem;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.n_stages; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+
+    // my two columns (2 tid, 2 tid + 1); a thread past the last pair computes a copy of the last pair, unwritten
+    const int n_pairs = p.out_w >> 1;
+    const bool active = tid < n_pairs;
+    const int ca = 2 * (active ? tid : n_pairs - 1), cb = ca + 1;
+    const int xmin = p.hbounds[2 * ca];
+    const int ob = p.hbounds[2 * cb] - xmin - 4 * DQ;                // first tap of B inside its quad range (>= 0: the plan checked)
+    uint32_t ka[3][NQ], kb[3][NQB];
+#pragma unroll
+    for (int g = 0; g < NQ; ++g) {
+        uint32_t l0 = 0, l1 = 0, l2 = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int t = 4 * g + b;
+            const uint32_t k = t < p.ksize_h ? uint32_t(p.hcoeffs[ca * p.ksize_h + t]) : 0u;
+            l0 |= (k & 0xffu) << (8 * b); l1 |= ((k >> 8) & 0xffu) << (8 * b); l2 |= ((k >> 16) & 0xffu) << (8 * b);
+        }
+        ka[0][g] = l0; ka[1][g] = l1; ka[2][g] = l2;
+    }
+#pragma unroll
+    for (int g = 0; g < NQB; ++g) {
+        uint32_t l0 = 0, l1 = 0, l2 = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int t = 4 * g + b - ob;
+            const uint32_t k = (t >= 0 && t < p.ksize_h) ? uint32_t(p.hcoeffs[cb * p.ksize_h + t]) : 0u;
+            l0 |= (k & 0xffu) << (8 * b); l1 |= ((k >> 8) & 0xffu) << (8 * b); l2 |= ((k >> 16) & 0xffu) << (8 * b);
+        }
+        kb[0][g] = l0; kb[1][g] = l1; kb[2][g] = l2;
+    }
+    __syncthreads();
+
+    const int total_stages = (n_rows + p.rows_per_stage - 1) / p.rows_per_stage;
+    auto stage_range = [&](int s, uint64_t &b0, uint64_t &b1) {
+        const int ra = r0 + s * p.rows_per_stage;
+        const int rb = min(ra + p.rows_per_stage, r1);
+        b0 = uint64_t(ra) * pitch;
+        b1 = uint64_t(rb) * pitch;
+    };
+    auto issue = [&](int s, int buf) { // thread 0 only, aligned images only
+        uint64_t b0, b1;
+        stage_range(s, b0, b1);
+        const uint64_t a0 = b0 & ~uint64_t(15);
+        uint64_t a1 = (b1 + 15) & ~uint64_t(15);
+        const uint64_t lim = img_bytes & ~uint64_t(15);
+        if (a1 > lim) a1 = lim;
+        const uint32_t bytes = a1 > a0 ? uint32_t(a1 - a0) : 0u;
+        if (bytes) {
+            mbar_arrive_expect_tx(&full_bar[buf], bytes);
+            bulk_g2s(ring + size_t(buf) * p.stage_bytes, img_ptr + a0, bytes, &full_bar[buf]);
+        } else {
+            mbar_arrive(&full_bar[buf]);
+        }
+    };
+    if (aligned && tid == 0) {
+        for (int s = 0; s < p.n_stages - 1 && s < total_stages; ++s) issue(s, s);
+    }
+
+    const int row_bytes = p.out_w * 3;
+    const uint32_t slot = p.out_slot ? p.out_slot[img] : uint32_t(img);
+    const uint32_t plane = uint32_t(p.out_h) * uint32_t(p.out_w);
+    const float mean0 = p.mean[0], mean1 = p.mean[1], mean2 = p.mean[2];
+    const float istd0 = p.inv_std[0], istd1 = p.inv_std[1], istd2 = p.inv_std[2];
+    // two adjacent pixels: 6 thumbnail bytes (2-byte aligned) and, per plane, two floats (8-byte aligned)
+    uint8_t *thumb_px = p.thumb + uint64_t(slot) * p.out_h * row_bytes + 3 * ca;
+    float *prev_px = p.preview ? p.preview + uint64_t(slot) * 3 * p.out_h * p.out_w + ca : nullptr;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(thumb_px) | uint32_t(row_bytes)) & 1u) == 0u &&
+                        (!prev_px || ((reinterpret_cast<uintptr_t>(prev_px) | (uint32_t(p.out_w) * 4u) | (plane * 4u)) & 7u) == 0u);
+    auto write_pair = [&](int oy, const uint32_t (&a)[3], const uint32_t (&b)[3]) {
+        uint8_t *tpx = thumb_px + uint32_t(oy) * uint32_t(row_bytes);
+        float *pp = prev_px ? prev_px + uint32_t(oy) * uint32_t(p.out_w) : nullptr;
+        if (vec_ok) {
+            uint16_t *t16 = reinterpret_cast<uint16_t *>(tpx);
+            t16[0] = uint16_t(a[0] | (a[1] << 8)); t16[1] = uint16_t(a[2] | (b[0] << 8)); t16[2] = uint16_t(b[1] | (b[2] << 8));
+            if (pp) {
+                *reinterpret_cast<float2 *>(pp) = make_float2(normalise(a[0], mean0, istd0), normalise(b[0], mean0, istd0));
+                *reinterpret_cast<float2 *>(pp + plane) = make_float2(normalise(a[1], mean1, istd1), normalise(b[1], mean1, istd1));
+                *reinterpret_cast<float2 *>(pp + 2 * plane) = make_float2(normalise(a[2], mean2, istd2), normalise(b[2], mean2, istd2));
+            }
+        } else {
+            tpx[0] = uint8_t(a[0]); tpx[1] = uint8_t(a[1]); tpx[2] = uint8_t(a[2]);
+            tpx[3] = uint8_t(b[0]); tpx[4] = uint8_t(b[1]); tpx[5] = uint8_t(b[2]);
+            if (pp) {
+                pp[0] = normalise(a[0], mean0, istd0); pp[1] = normalise(b[0], mean0, istd0);
+                pp[plane] = normalise(a[1], mean1, istd1); pp[plane + 1] = normalise(b[1], mean1, istd1);
+                pp[2 * plane] = normalise(a[2], mean2, istd2); pp[2 * plane + 1] = normalise(b[2], mean2, istd2);
+            }
+        }
+    };
+
+    // scatter-form vertical pass: three output rows in flight per column, accumulators never reset (see the band kernel)
+    uint32_t vaa[3][3], vba[3][3], vab[3][3], vbb[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { vaa[j][c] = vab[j][c] = uint32_t(kRound); vba[j][c] = vbb[j][c] = 0u; }
+
+    int buf = 0, ibuf = p.n_stages - 1;
+    uint32_t parity = 0;
+    for (int s = 0; s < total_stages; ++s) {
+        uint8_t *sbuf = ring + size_t(buf) * p.stage_bytes;
+        uint64_t b0, b1;
+        stage_range(s, b0, b1);
+        const uint64_t a0 = b0 & ~uint64_t(15);
+        if (aligned) {
+            if (tid == 0 && s + p.n_stages - 1 < total_stages) issue(s + p.n_stages - 1, ibuf);
+            mbar_wait(&full_bar[buf], parity);
+            const uint64_t lim = img_bytes & ~uint64_t(15);
+            if (b1 > lim) {
+                for (uint64_t b = max(lim, a0) + tid; b < b1; b += blockDim.x) sbuf[b - a0] = img_ptr[b];
+                __syncthreads();
+            }
+        } else {
+            for (uint64_t b = b0 + tid; b < b1; b += blockDim.x) sbuf[b - a0] = img_ptr[b];
+            __syncthreads();
+        }
+
+        const int ra = r0 + s * p.rows_per_stage;
+        const int rb = min(ra + p.rows_per_stage, r1);
+        {
+            const int4 *vsp = p.vscat + ra;
+            uint32_t src = smem_u32(sbuf) + uint32_t(uint64_t(ra) * pitch - a0) + 3u * xmin;
+            for (int r = ra; r < rb; ++r, src += uint32_t(pitch)) {
+                const uint32_t base = src & ~3u;
+                const uint32_t sh = src << 3;
+                uint32_t w[3 * NU + 1];
+#pragma unroll
+                for (int j = 0; j < 3 * NU + 1; ++j)
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[j]) : "r"(base + 4u * j));
+                uint32_t aa[3][3], ab[3][3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { aa[c][0] = ab[c][0] = uint32_t(kRound); aa[c][1] = aa[c][2] = ab[c][1] = ab[c][2] = 0; }
+#pragma unroll
+                for (int g = 0; g < NU; ++g) {
+                    const uint32_t w0 = __funnelshift_r(w[3 * g], w[3 * g + 1], sh);
+                    const uint32_t w1 = __funnelshift_r(w[3 * g + 1], w[3 * g + 2], sh);
+                    const uint32_t w2 = __funnelshift_r(w[3 * g + 2], w[3 * g + 3], sh);
+                    uint32_t px[3];
+                    px[0] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+                    px[1] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+                    px[2] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+                    if (g < NQ) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            aa[c][0] = __dp4a(px[c], ka[0][g], aa[c][0]);
+                            aa[c][1] = __dp4a(px[c], ka[1][g], aa[c][1]);
+                            aa[c][2] = __dp4a(px[c], ka[2][g], aa[c][2]);
+                        }
+                    }
+                    if (g >= DQ && g < DQ + NQB) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            ab[c][0] = __dp4a(px[c], kb[0][g - DQ], ab[c][0]);
+                            ab[c][1] = __dp4a(px[c], kb[1][g - DQ], ab[c][1]);
+                            ab[c][2] = __dp4a(px[c], kb[2][g - DQ], ab[c][2]);
+                        }
+                    }
+                }
+                uint32_t oa[3], ob_[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    oa[c] = to_u8(aa[c][0] + (aa[c][1] << 8) + (aa[c][2] << 16));
+                    ob_[c] = to_u8(ab[c][0] + (ab[c][1] << 8) + (ab[c][2] << 16));
+                }
+                const int4 e = __ldg(vsp++);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    vaa[0][c] += oa[c] * uint32_t(e.x); vaa[1][c] += oa[c] * uint32_t(e.y); vaa[2][c] += oa[c] * uint32_t(e.z);
+                    vab[0][c] += ob_[c] * uint32_t(e.x); vab[1][c] += ob_[c] * uint32_t(e.y); vab[2][c] += ob_[c] * uint32_t(e.z);
+                }
+                if (e.w) {
+                    const int oy = e.w >> 2;
+                    const bool mine = oy >= oy0 && oy < oy1 && active;
+                    auto finish = [&](uint32_t (&xa)[3], uint32_t (&ya)[3], uint32_t (&xb)[3], uint32_t (&yb)[3]) {
+                        if (mine) {
+                            const uint32_t pa[3] = {to_u8(xa[0] - ya[0]), to_u8(xa[1] - ya[1]), to_u8(xa[2] - ya[2])};
+                            const uint32_t pb[3] = {to_u8(xb[0] - yb[0]), to_u8(xb[1] - yb[1]), to_u8(xb[2] - yb[2])};
+                            write_pair(oy, pa, pb);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { ya[c] = xa[c] - uint32_t(kRound); yb[c] = xb[c] - uint32_t(kRound); }
+                    };
+                    const int sl = e.w & 3;
+                    if (sl == 1) finish(vaa[0], vba[0], vab[0], vbb[0]);
+                    else if (sl == 2) finish(vaa[1], vba[1], vab[1], vbb[1]);
+                    else finish(vaa[2], vba[2], vab[2], vbb[2]);
+                }
+            }
+        }
+        __syncthreads();
+        if (++buf == p.n_stages) { buf = 0; parity ^= 1u; }
+        if (++ibuf == p.n_stages) ibuf = 0;
+    }
+}
+
 // One thread per output pixel (all three channels), any shape, any alignment.
 __global__ void __launch_bounds__(256)
 resize_generic_kernel(const ResizeParams p, uint32_t n) {
@@ -449,6 +684,20 @@ static int pick_quads_bucket(int max_taps) {
     for (int b : buckets)
         if (max_taps <= b) return b;
     return 0;
+}
+
+// The (tap capacity, quad offset, quad count) triples of resize_pairs_kernel that are built.  (16, 1, 5) is 1080p ->
+// 256 wide, BASELINE config 2: columns alternately 7 and 8 pixels apart, so the odd column genuinely needs five quads.
+// Measured against the band kernel in one call (tools/resize_ab.sh): 1080p 3.12 ms against 3.38 ms (-7.5 %); 2048^2,
+// which maps to the same triple but has every window quad-aligned (scale 8), was 4 % SLOWER (the fifth quad of the odd
+// column is all zeros there), so the plan takes the pair kernel only for non-integer horizontal scales.  Other plans
+// use the band kernel.
+#define B2_PAIRS_VARIANTS(X) X(0, 16, 1, 5)
+static int pairs_variant(int kq, int dq, int nqb) {
+#define B2_X(I, KQ, DQ, NQB) if (kq == KQ && dq == DQ && nqb == NQB) return I;
+    B2_PAIRS_VARIANTS(B2_X)
+#undef B2_X
+    return -1;
 }
 
 template <int KQ>
@@ -581,6 +830,37 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
             }
         }
     }
+    // ---- pair kernel eligibility: even out_w, scatter form available, and (KQ, DQ, NQB) among the built instantiations
+    pl->pair = 0;
+    if (pl->scat && out_w % 2 == 0 && out_w >= 64 && in_w % out_w != 0) {
+        int dq = 1 << 30, hi = 0;
+        for (int x = 0; x + 1 < out_w; x += 2) {
+            const int ob = pl->h.bounds[2 * (x + 1)] - pl->h.bounds[2 * x];
+            dq = std::min(dq, ob / 4);
+        }
+        for (int x = 0; x + 1 < out_w; x += 2) {
+            const int ob = pl->h.bounds[2 * (x + 1)] - pl->h.bounds[2 * x];
+            hi = std::max(hi, ob - 4 * dq + pl->h.bounds[2 * (x + 1) + 1]);
+        }
+        const int nqb = (hi + 3) / 4;
+        const bool built = pairs_variant(pl->q_bucket, dq, nqb) >= 0;
+        if (built && !getenv("B2_RESIZE_NO_PAIRS")) {
+            pl->pair_dq = dq; pl->pair_nqb = nqb;
+            pl->pair_threads = ((out_w / 2 + 31) / 32) * 32;
+            const int nu = std::max(pl->q_bucket / 4, dq + nqb);
+            const int over = 12 * nu + 4 + 64;
+            size_t pair_budget = (pl->q_bucket <= 20 ? 52 : 72) * 1024;      // four (three: wide taps need > 128 registers) CTAs of four warps per SM
+            if (const char *e = getenv("B2_RESIZE_PAIR_SMEM_KB")) pair_budget = size_t(atoi(e)) * 1024;
+            int rs = rps_cap;
+            for (; rs >= 1; --rs) {
+                pl->rps_pair = rs;
+                pl->stage_bytes_pair = ((rs * pitch + 32 + over + 127) / 128) * 128;
+                pl->smem_pair = size_t(pl->n_stages) * pl->stage_bytes_pair + 64;
+                if (pl->smem_pair <= pair_budget) break;
+            }
+            pl->pair = rs >= 1 && pl->smem_pair <= 220 * 1024;
+        }
+    }
     *plan_out = pl;
     return B2_OK;
 }
@@ -672,6 +952,35 @@ extern "C" int b2_resize_normalize_batch(const b2_resize_plan *pl, const uint8_t
         p.vscat = pl->d_vscat;
         p.rows_per_stage = pl->rps_scat; p.stage_bytes = pl->stage_bytes_scat;
         smem = pl->smem_scat;
+    }
+    if (vscat && pl->pair) {
+        p.rows_per_stage = pl->rps_pair; p.stage_bytes = pl->stage_bytes_pair;
+        const int variant = pairs_variant(pl->q_bucket, pl->pair_dq, pl->pair_nqb);
+        static std::mutex pmu;
+        static size_t pair_attr[64][8];
+        cudaError_t pe = cudaSuccess;
+        {
+            std::lock_guard<std::mutex> lock(pmu);
+            if (pair_attr[pl->device & 63][variant] < pl->smem_pair) {
+#define B2_X(I, KQ, DQ, NQB)                                                                                                    \
+                if (variant == I) {                                                                                             \
+                    pe = cudaFuncSetAttribute(resize_pairs_kernel<KQ, DQ, NQB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem_pair)); \
+                    if (pe == cudaSuccess)                                                                                      \
+                        pe = cudaFuncSetAttribute(resize_pairs_kernel<KQ, DQ, NQB>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                                  cudaSharedmemCarveoutMaxShared);                                             \
+                }
+                B2_PAIRS_VARIANTS(B2_X)
+#undef B2_X
+                if (pe == cudaSuccess) pair_attr[pl->device & 63][variant] = pl->smem_pair;
+            }
+        }
+        B2_CUDA_CHECK(pe);
+        const uint32_t grid = n * uint32_t(p.n_bands);
+#define B2_X(I, KQ, DQ, NQB) if (variant == I) resize_pairs_kernel<KQ, DQ, NQB><<<grid, pl->pair_threads, pl->smem_pair, st>>>(p);
+        B2_PAIRS_VARIANTS(B2_X)
+#undef B2_X
+        B2_LAUNCH_CHECK("resize_pairs_kernel");
+        return B2_OK;
     }
     const size_t smem_attr = std::max(pl->smem_max, pl->smem_scat);
     static std::mutex mu;
