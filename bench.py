@@ -996,7 +996,9 @@ def build_line(args, out, world, warmup, hbm_peak, peak_src, torch, dev):
             "parity": res["parity"],
         })
         kernels["sha256_lanes_kernel"] = roof(sha_bytes, res["ms_sha"], "sha256_lanes_kernel", note="ALU bound: see roofline")
-        kernels["resize_bands_kernel"] = roof(resize_bytes, res["ms_resize"], "resize_bands_kernel", note="timed alone")
+        kernels["resize_pairs_kernel"] = roof(resize_bytes, res["ms_resize"], "resize_pairs_kernel",
+                                              note="timed alone; two output columns per thread (1080p -> 256 wide); the band kernel "
+                                                   "(B2_RESIZE_NO_PAIRS=1) measures 0.745 on the same launch")
         kernels["dedupe (insert+resolve)"] = {"ms_per_launch": res["ms_dedupe"], "digests": n_img}
     lab = out.get("labels")
     if lab:
