@@ -298,7 +298,22 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(PeerReduceDesc *d, 
 // Collective and blocking (every rank calls it once, with the same max_values): allocates this rank's mailbox, exchanges
 // the CUDA IPC handles through the communicator and maps the peers' mailboxes.  One process per GPU, all GPUs of one box
 // with peer access (NVLink / NVSwitch).
+namespace b2 {
+static int enable_peer_reduce_impl(b2_comm *c, uint32_t max_values);
+}
 extern "C" int b2_comm_enable_peer_reduce(b2_comm *c, uint32_t max_values) {
+    const int rc = b2::enable_peer_reduce_impl(c, max_values);
+    if (rc != B2_OK && c && c->d_peer == nullptr) {          // failed half way: give back what was allocated and mapped
+        for (int q = 0; q < c->world && q < b2::kPeerMaxWorld; ++q)
+            if (c->peer_maps[q]) { cudaIpcCloseMemHandle(c->peer_maps[q]); c->peer_maps[q] = nullptr; }
+        cudaFree(c->d_mailbox);
+        c->d_mailbox = nullptr;
+        c->peer_cap = 0;
+        cudaGetLastError();
+    }
+    return rc;
+}
+static int b2::enable_peer_reduce_impl(b2_comm *c, uint32_t max_values) {
     using namespace b2;
     B2_REQUIRE(c != nullptr && max_values >= 1 && max_values <= (1u << 20), "b2_comm_enable_peer_reduce: bad argument");
     B2_REQUIRE(c->world <= kPeerMaxWorld, "b2_comm_enable_peer_reduce: at most %d ranks", kPeerMaxWorld);
@@ -335,13 +350,21 @@ extern "C" int b2_comm_enable_peer_reduce(b2_comm *c, uint32_t max_values) {
         h.flags[q] = reinterpret_cast<uint32_t *>(base);
         h.mail[q] = reinterpret_cast<unsigned long long *>(base + flag_bytes);
     }
-    B2_CUDA_CHECK(cudaMalloc(&c->d_peer, sizeof(h)));
-    B2_CUDA_CHECK(cudaMemcpy(c->d_peer, &h, sizeof(h), cudaMemcpyHostToDevice));
-    c->peer_cap = cap;
+    PeerReduceDesc *d_desc = nullptr;
+    B2_CUDA_CHECK(cudaMalloc(&d_desc, sizeof(h)));
+    cudaError_t ce = cudaMemcpy(d_desc, &h, sizeof(h), cudaMemcpyHostToDevice);
     // nobody writes into a mailbox before every rank has zeroed and mapped: one more (tiny) collective as a barrier
     int64_t *d_one = reinterpret_cast<int64_t *>(c->d_mailbox + flag_bytes);
-    B2_NCCL_CHECK(api->AllReduce(d_one, d_one, 1, ncclInt64, ncclSum, c->comm, nullptr));
-    B2_CUDA_CHECK(cudaStreamSynchronize(nullptr));
+    ncclResult_t nr = ce == cudaSuccess ? api->AllReduce(d_one, d_one, 1, ncclInt64, ncclSum, c->comm, nullptr) : ncclSuccess;
+    if (ce == cudaSuccess && nr == ncclSuccess) ce = cudaStreamSynchronize(nullptr);
+    if (ce == cudaSuccess && nr == ncclSuccess) ce = cudaMemset(d_one, 0, 8);
+    if (ce != cudaSuccess || nr != ncclSuccess) {
+        cudaFree(d_desc);
+        return ce != cudaSuccess ? fail(B2_ERR_CUDA, "b2_comm_enable_peer_reduce: %s", cudaGetErrorString(ce))
+                                 : fail(B2_ERR_NCCL, "b2_comm_enable_peer_reduce: %s", api->GetErrorString(nr));
+    }
+    c->d_peer = d_desc;
+    c->peer_cap = cap;
     return B2_OK;
 }
 

@@ -95,3 +95,36 @@ def test_encode_label_rows_on_reference_fixture_rows(ref_labels):
     img2, cls2, _ = encode_label_rows(rows, hashes[1:], options[1:])
     assert (img2 == -1).sum() == sum(r["id_img"] == hashes[0] for r in rows)
     assert (cls2 == 255).sum() == sum(r["id_opc"] == options[0] for r in rows)
+
+
+def test_agreement_histogram_is_the_integer_form_of_sum_pi():
+    """The histogram the tally pass accumulates (graft-defined) against the textbook definition: sum_i P_i over images
+    with n_i >= 2 equals sum_n bin[n] / (n (n - 1)), so the general-n kappa computed from INTEGERS (host code of the
+    product, no GPU involved) equals the count-matrix formula; shards add up bin by bin."""
+    import numpy as np
+
+    from ics_b200.labels import fleiss_kappa_from_hist, sum_pi_from_hist
+    from oracle import agreement_hist, fleiss_kappa_general
+    rng = np.random.default_rng(8)
+    counts = rng.integers(0, 7, size=(5000, 12)).astype(np.int32)
+    counts[::5] = 0
+    counts[1::5, 1:] = 0                                               # single-class images
+    counts[3] = 0
+    counts[3, 0] = 1                                                   # n_i = 1: contributes nothing
+    h = agreement_hist(counts)
+    c = counts.astype(np.int64)
+    n_i = c.sum(1)
+    m = n_i >= 2
+    want = float(((c[m] ** 2).sum(1) - n_i[m]).astype(np.float64).__truediv__((n_i[m] * (n_i[m] - 1)).astype(np.float64)).sum())
+    assert h[0] == 0 and h[1] == 0 and abs(sum_pi_from_hist(h) - want) <= 1e-9 * want
+    kg = fleiss_kappa_from_hist(c.sum(0), int(n_i.sum()), int(m.sum()), h)
+    assert abs(kg - fleiss_kappa_general(counts)) <= 1e-12 * abs(kg)
+    assert np.array_equal(agreement_hist(counts[:2000]) + agreement_hist(counts[2000:]), h)
+    big = np.zeros((2, 3), dtype=np.int32)
+    big[0] = (600, 500, 0)                                             # 1 100 ratings: past the last bin
+    big[1] = (2, 1, 0)
+    hb = agreement_hist(big)
+    assert hb[0] == 1 and hb[3] == 2 * 2 + 1 - 3
+    import pytest
+    with pytest.raises(ValueError):
+        sum_pi_from_hist(hb)
