@@ -688,11 +688,12 @@ static int pick_quads_bucket(int max_taps) {
 
 // The (tap capacity, quad offset, quad count) triples of resize_pairs_kernel that are built.  (16, 1, 5) is 1080p ->
 // 256 wide, BASELINE config 2: columns alternately 7 and 8 pixels apart, so the odd column genuinely needs five quads.
-// Measured against the band kernel in one call (tools/resize_ab.sh): 1080p 3.12 ms against 3.38 ms (-7.5 %); 2048^2,
-// which maps to the same triple but has every window quad-aligned (scale 8), was 4 % SLOWER (the fifth quad of the odd
-// column is all zeros there), so the plan takes the pair kernel only for non-integer horizontal scales.  Other plans
+// (36, 2, 10) is 4K (3840 wide) -> 256, BASELINE config 5.  Measured against the band kernel in one call
+// (tools/resize_ab.sh, tools/resize_shapes.py): 1080p 3.12 ms against 3.38 ms (-7.5 %), 4K 1.40 against 1.63 ms (-14 %);
+// 2048^2, which maps to the first triple, was 4 % SLOWER because its lanes are 12 words apart and collide 4-way in the
+// shared-memory banks: the plan checks the bank spread of the pair mapping before taking this kernel.  Other plans
 // use the band kernel.
-#define B2_PAIRS_VARIANTS(X) X(0, 16, 1, 5)
+#define B2_PAIRS_VARIANTS(X) X(0, 16, 1, 5) X(1, 36, 2, 10)
 static int pairs_variant(int kq, int dq, int nqb) {
 #define B2_X(I, KQ, DQ, NQB) if (kq == KQ && dq == DQ && nqb == NQB) return I;
     B2_PAIRS_VARIANTS(B2_X)
@@ -832,7 +833,7 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
     }
     // ---- pair kernel eligibility: even out_w, scatter form available, and (KQ, DQ, NQB) among the built instantiations
     pl->pair = 0;
-    if (pl->scat && out_w % 2 == 0 && out_w >= 64 && in_w % out_w != 0) {
+    if (pl->scat && out_w % 2 == 0 && out_w >= 64) {
         int dq = 1 << 30, hi = 0;
         for (int x = 0; x + 1 < out_w; x += 2) {
             const int ob = pl->h.bounds[2 * (x + 1)] - pl->h.bounds[2 * x];
@@ -843,7 +844,22 @@ extern "C" int b2_resize_plan_create(int in_h, int in_w, int out_h, int out_w, b
             hi = std::max(hi, ob - 4 * dq + pl->h.bounds[2 * (x + 1) + 1]);
         }
         const int nqb = (hi + 3) / 4;
-        const bool built = pairs_variant(pl->q_bucket, dq, nqb) >= 0;
+        // Shared-memory banks: the 32 lanes of a warp read their union windows 2 x scale x 3 bytes apart.  1080p (45 bytes) and
+        // 4K (90 bytes) spread over the banks; 2048^2 (48 bytes = 12 words) lands on 8 banks, 4096^2 (24 words) on 4, and
+        // the pair kernel then LOSES to the band kernel (measured: 2048^2 1.428 against 1.374 ms).  Worst number of
+        // distinct words per bank over the warps of a row decides.
+        int worst = 1;
+        for (int w0 = 0; w0 < out_w / 2; w0 += 32) {
+            int words[32][32], cnt[32] = {};
+            for (int l = 0; l < 32 && w0 + l < out_w / 2; ++l) {
+                const int word = (3 * pl->h.bounds[2 * 2 * (w0 + l)]) >> 2, bank = word & 31;
+                bool seen = false;
+                for (int i = 0; i < cnt[bank]; ++i) seen = seen || words[bank][i] == word;
+                if (!seen) words[bank][cnt[bank]++] = word;
+            }
+            for (int b = 0; b < 32; ++b) worst = std::max(worst, cnt[b]);
+        }
+        const bool built = pairs_variant(pl->q_bucket, dq, nqb) >= 0 && worst <= 3;
         if (built && !getenv("B2_RESIZE_NO_PAIRS")) {
             pl->pair_dq = dq; pl->pair_nqb = nqb;
             pl->pair_threads = ((out_w / 2 + 31) / 32) * 32;
