@@ -688,12 +688,13 @@ static int pick_quads_bucket(int max_taps) {
 
 // The (tap capacity, quad offset, quad count) triples of resize_pairs_kernel that are built.  (16, 1, 5) is 1080p ->
 // 256 wide, BASELINE config 2: columns alternately 7 and 8 pixels apart, so the odd column genuinely needs five quads.
-// (36, 2, 10) is 4K (3840 wide) -> 256, BASELINE config 5.  Measured against the band kernel in one call
+// (36, 2, 10) is 4K (3840 wide) -> 256, BASELINE config 5; (4, 0, 2) and (8, 0, 3) are 512 and 1024 wide (configs 1, 3:
+// 2.71 against 2.87 ms and 1.61 against 1.72 ms per ~6 GB of images).  Measured against the band kernel in one call
 // (tools/resize_ab.sh, tools/resize_shapes.py): 1080p 3.12 ms against 3.38 ms (-7.5 %), 4K 1.40 against 1.63 ms (-14 %);
 // 2048^2, which maps to the first triple, was 4 % SLOWER because its lanes are 12 words apart and collide 4-way in the
 // shared-memory banks: the plan checks the bank spread of the pair mapping before taking this kernel.  Other plans
 // use the band kernel.
-#define B2_PAIRS_VARIANTS(X) X(0, 16, 1, 5) X(1, 36, 2, 10)
+#define B2_PAIRS_VARIANTS(X) X(0, 16, 1, 5) X(1, 36, 2, 10) X(2, 4, 0, 2) X(3, 8, 0, 3)
 static int pairs_variant(int kq, int dq, int nqb) {
 #define B2_X(I, KQ, DQ, NQB) if (kq == KQ && dq == DQ && nqb == NQB) return I;
     B2_PAIRS_VARIANTS(B2_X)
