@@ -241,7 +241,9 @@ def run_reference(args):
         "impl": "reference", "metric": "ingest images/s", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
-        "config": workload_config(args.gpus, n_img, "host memory; bounded sample"),
+        # the graft arm's config (the workload both arms are measured on); what this arm actually ran per step — a bounded
+        # sample of it in host memory — is stated in cpu_baseline.sample
+        "config": workload_config(args.gpus, args.images_per_gpu or FULL_IMAGES_PER_GPU, RESIDENT_INPUTS),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "labels": {"value": lab_v, "unit": "rows/s", "cores": min(cores, 16), "sample": "10M rows, N=100k, k=50"},
@@ -249,6 +251,10 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+RESIDENT_INPUTS = ("resident in HBM, generated on device (content keyed by listing position), "
+                   "20 % duplicates of the GLOBAL listing")
 
 
 def workload_config(n_gpus, images_per_gpu, residency):
@@ -979,8 +985,7 @@ def build_line(args, out, world, warmup, hbm_peak, peak_src, torch, dev):
         m = ncu.get("sha256_lanes_kernel") or {}
         line.update({
             "value": res["value"], "ms_per_step": res["ms"] / args.steps,
-            "config": workload_config(world, n_img, "resident in HBM, generated on device (content keyed by listing position), "
-                                                     "20 % duplicates of the GLOBAL listing"),
+            "config": workload_config(world, n_img, RESIDENT_INPUTS),
             "clocks": clocks, "gpu_launches": res["launches"], "step_ms_rank0": res["step_ms"],
             "roofline": {
                 "kernel": "sha256_lanes_kernel", "bound": "int32 ALU pipe", "achieved": alu_ach, "peak": alu_peak,
