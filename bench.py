@@ -470,7 +470,6 @@ def run_graft(args):
         max_imgs = max(args.e2e_images, C5_PER_GPU, args.c3_images, 1000)
         ring = IngestRing(ring_bytes=ring_bytes, chunk_bytes=args.chunk_mb << 20, max_listings=args.listings,
                           max_images=max_imgs, out_h=OUT, out_w=OUT, want_preview=True, device=local_rank)
-        stage = torch.empty(64 << 20, dtype=torch.uint8, device=dev)      # device scratch to build host inputs from
 
     def make_host_listing(shapes, content_ids):
         """Page-locked host buffer holding the listing's images back to back (generated on the device image by
@@ -712,7 +711,6 @@ def run_graft(args):
 
     if ring is not None:
         ring.close()
-        del stage
         torch.cuda.empty_cache()
 
     # =========================================================================================================
