@@ -114,9 +114,16 @@ class _HashCoalescer:
             for e in batch:
                 e[1] = hexes[o:o + len(e[0])]
                 o += len(e[0])
-        except BaseException as err:  # noqa: BLE001 - every waiter of this round gets the error
-            for e in batch:
-                e[2] = err
+        except BaseException as err:  # noqa: BLE001
+            if len(batch) == 1:
+                batch[0][2] = err
+            else:                                             # one caller's bad input must not fail the others: one by one
+                for e in batch:
+                    try:
+                        e[1] = sha256_host(e[0], device)[1]
+                        self.launches += 1
+                    except BaseException as own:  # noqa: BLE001 - reaches the caller that caused it
+                        e[2] = own
         for e in batch:
             e[3].set()
 

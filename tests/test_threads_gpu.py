@@ -96,3 +96,36 @@ def test_concurrent_single_file_hashes_share_launches():
     with pytest.raises(Exception):
         hostapi.hash_batch([None])                          # an error reaches the caller that caused it
     assert hostapi.hash_batch([b"abc"]) == ["ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"]
+
+
+def test_coalesced_hashes_keep_errors_with_their_caller():
+    """A caller that hands in garbage fails alone: calls merged into the same launch still get their digests."""
+    import hashlib
+
+    from ics_b200 import hostapi
+    hostapi.hash_batch([b"warm-up"])
+    results, errors = {}, {}
+    gate = threading.Barrier(4)
+
+    def good(i):
+        gate.wait()
+        for j in range(30):
+            blob = bytes([i, j]) * 1000
+            results[(i, j)] = hostapi.hash_batch([blob]) == [hashlib.sha256(blob).hexdigest()]
+
+    def bad():
+        gate.wait()
+        for _ in range(30):
+            try:
+                hostapi.hash_batch([None])
+                errors["no-raise"] = True
+            except Exception:  # noqa: BLE001
+                errors["raised"] = errors.get("raised", 0) + 1
+
+    threads = [threading.Thread(target=good, args=(i,)) for i in range(3)] + [threading.Thread(target=bad)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert len(results) == 90 and all(results.values())
+    assert errors == {"raised": 30}
