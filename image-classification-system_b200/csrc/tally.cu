@@ -619,7 +619,7 @@ fleiss_partials_kernel(const int32_t *__restrict__ counts, uint32_t n_images, ui
                        unsigned long long *__restrict__ g_partials, double *__restrict__ sum_pi_out,
                        double *__restrict__ block_sums, unsigned int *__restrict__ ticket,
                        unsigned long long *__restrict__ g_hist) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const TallySmem sm = carve_smem(smem_raw, tile_images, k);
     int32_t *tile = sm.tile;
     double *s_dred = sm.dred;
